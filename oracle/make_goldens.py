@@ -1,0 +1,281 @@
+"""TEST INFRASTRUCTURE ONLY -- generates ``tests/golden/*.npz`` by running the UNMODIFIED reference
+classes (loaded by ``oracle/refshim.py`` from /root/reference, commit 789288c) on seeded synthetic inputs.
+
+Run in the build container (the only place /root/reference exists):
+
+    python -m oracle.make_goldens            # all fixtures
+    python -m oracle.make_goldens knrm drmm  # a subset
+
+Inputs come from ``capreolus_b200/synthetic.py``; the 36 MB embedding table and BERT-base weights are not
+stored -- they are re-derived from their seeds and a checksum of each is stored instead.
+"""
+from __future__ import annotations
+
+import contextlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from capreolus_b200 import synthetic
+from oracle import refshim
+
+GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
+SHAPES = {
+    # name: (B, Q, D, V, E, table_seed, input_seed)
+    "full": (64, 32, 512, 30000, 300, 0, 1),  # BASELINE.json configs[0]
+    "small": (6, 8, 40, 500, 50, 10, 11),
+    "odd": (3, 5, 77, 211, 36, 20, 21),  # nothing a multiple of a tile size
+}
+
+
+def table_checksum(table: np.ndarray) -> np.ndarray:
+    return np.array([table.astype(np.float64).sum(), np.abs(table.astype(np.float64)).sum(), float(table[-1, -1])])
+
+
+def _state_np(model, skip=("embedding.weight",)):
+    return {f"state/{k}": v.detach().cpu().numpy() for k, v in model.state_dict().items() if not any(s in k for s in skip)}
+
+
+def _inputs(shape_name, oov=True):
+    B, Q, D, V, E, tseed, iseed = SHAPES[shape_name]
+    table = synthetic.embedding_table(V, E, seed=tseed)
+    batch = synthetic.parity_batch(B, Q, D, V, seed=iseed, oov=oov)
+    return table, batch
+
+
+def _common(shape_name, table, batch):
+    B, Q, D, V, E, tseed, iseed = SHAPES[shape_name]
+    out = {k: (v.astype(np.int32) if v.dtype == np.int64 else v) for k, v in batch.items()}
+    out.update(shape=np.array([B, Q, D, V, E]), table_seed=np.array(tseed), input_seed=np.array(iseed),
+               table_checksum=table_checksum(table), reference_commit=np.array(refshim.REFERENCE_COMMIT))
+    return out
+
+
+def _t(batch):
+    return {k: torch.from_numpy(v) for k, v in batch.items()}
+
+
+def make_knrm():
+    ref = refshim.load_rerankers()
+    for shape_name in SHAPES:
+        table, batch = _inputs(shape_name)
+        B, Q, D, V, E, *_ = SHAPES[shape_name]
+        tb = _t(batch)
+        out = _common(shape_name, table, batch)
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        for variant, cfg in {
+            "default": dict(gradkernels=True, scoretanh=False, singlefc=True, finetune=False),
+            "twofc": dict(gradkernels=True, scoretanh=False, singlefc=False, finetune=False),
+            "tanh": dict(gradkernels=True, scoretanh=True, singlefc=True, finetune=False),
+        }.items():
+            torch.manual_seed(100)
+            # go through the reference Reranker wrapper: build_model / score / test (KNRM.py:81-101)
+            rr = ref.KNRM.KNRM(cfg, provide={"extractor": ext})
+            model = rr.build_model().eval()
+            if variant == "default" and shape_name != "full":
+                # distinct, non-default kernel parameters so mu/sigma plumbing is really checked
+                with torch.no_grad():
+                    for i, k in enumerate(model.kernels.kernels):
+                        k.mu.add_(0.013 * (i - 4))
+                        k.sigma.mul_(1.0 + 0.05 * i)
+            with torch.no_grad():
+                pos, neg = rr.score(tb)
+                assert torch.equal(rr.test(tb), pos)
+                if variant == "default":
+                    sim = model.simmat(tb["query"], tb["posdoc"])
+                    kern = model.kernels(sim)
+                    soft_tf = kern.sum(dim=3)  # [B,K,Q]
+                    out["sim_first2"] = sim[:2].numpy()
+                    out["soft_tf"] = soft_tf.numpy()
+                    out["row_live"] = (sim.sum(dim=2) != 0.0).numpy()
+            out[f"{variant}/pos"] = pos.numpy()
+            out[f"{variant}/neg"] = neg.numpy()
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model).items()})
+        np.savez_compressed(GOLDEN / f"knrm_{shape_name}.npz", **out)
+        print("knrm", shape_name, out["default/pos"][:4])
+
+
+def make_drmm():
+    ref = refshim.load_rerankers()
+    for shape_name in SHAPES:
+        table, batch = _inputs(shape_name, oov=False)  # DRMM.py:109 cannot take negative (OOV) query ids
+        B, Q, D, V, E, *_ = SHAPES[shape_name]
+        tb = _t(batch)
+        out = _common(shape_name, table, batch)
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        for variant, cfg in {
+            "default": dict(nbins=29, nodes=5, histType="LCH", gateType="IDF"),
+            "nh": dict(nbins=29, nodes=5, histType="NH", gateType="IDF"),
+            "ch_tv": dict(nbins=11, nodes=7, histType="CH", gateType="TV"),
+        }.items():
+            torch.manual_seed(200)
+            rr = ref.DRMM.DRMM(cfg, provide={"extractor": ext})
+            model = rr.build_model().eval()
+            with torch.no_grad():
+                # the default init (|w| <= 0.1 / 0.01) makes every score ~bias; spread the weights so that
+                # the histogram and the gate actually matter in the parity check
+                model.ffw[0].weight.mul_(10.0)
+                model.ffw[2].weight.mul_(10.0)
+                model.gates.weight.mul_(40.0)
+                pos, neg = rr.score(tb)
+                if variant == "default":
+                    d_mask = (tb["posdoc"] != 0).float()
+                    out["hist"] = model._hist_map(tb["query"], tb["posdoc"], d_mask).numpy()
+            out[f"{variant}/pos"] = pos.numpy()
+            out[f"{variant}/neg"] = neg.numpy()
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model).items()})
+        np.savez_compressed(GOLDEN / f"drmm_{shape_name}.npz", **out)
+        print("drmm", shape_name, out["default/pos"][:4])
+
+
+def make_pacrr():
+    ref = refshim.load_rerankers()
+    for shape_name in SHAPES:
+        table, batch = _inputs(shape_name)
+        B, Q, D, V, E, *_ = SHAPES[shape_name]
+        tb = _t(batch)
+        out = _common(shape_name, table, batch)
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        for variant, cfg in {
+            "default": dict(mingram=1, maxgram=3, nfilters=32, idf=True, kmax=2, combine=32, nonlinearity="relu"),
+            "noidf_tanh": dict(mingram=1, maxgram=3, nfilters=32, idf=False, kmax=2, combine=32, nonlinearity="tanh"),
+            "wide": dict(mingram=2, maxgram=3, nfilters=16, idf=True, kmax=3, combine=24, nonlinearity="none"),
+        }.items():
+            torch.manual_seed(300)
+            rr = ref.PACRR.PACRR(cfg, provide={"extractor": ext})
+            model = rr.build_model().eval()
+            with torch.no_grad():
+                idf_arg = {**tb, "query_idf": refshim.pacrr_idf(tb["query_idf"])}  # PACRR.py:49 work-around
+                pos, neg = rr.score(idf_arg)
+                if variant == "default":
+                    sim = model.simmat(tb["query"], tb["posdoc"])
+                    out["topk"] = torch.cat([ng(sim) for ng in model.ngrams], dim=2).numpy()  # [B,Q,6]
+            out[f"{variant}/pos"] = pos.numpy()
+            out[f"{variant}/neg"] = neg.numpy()
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model).items()})
+        np.savez_compressed(GOLDEN / f"pacrr_{shape_name}.npz", **out)
+        print("pacrr", shape_name, out["default/pos"][:4])
+
+
+BERT_CONFIGS = {
+    # name: (BertConfig kwargs, N docs, P passages, L, qlen, weight seed, input seed)
+    "tiny": (dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, vocab_size=1000,
+                  max_position_embeddings=64), 6, 3, 48, 6, 0, 3),
+    "mid": (dict(hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=1024, vocab_size=5000,
+                 max_position_embeddings=512, initializer_range=0.08), 4, 2, 200, 16, 0, 5),
+    "base": (dict(), 4, 1, 512, 32, 0, 3),  # BERT-base: BASELINE.json configs[3] (monoBERT: P=1)
+}
+
+
+def bert_weight_checksum(model) -> np.ndarray:
+    tot = 0.0
+    for v in model.state_dict().values():
+        if v.dtype.is_floating_point:
+            tot += float(v.double().abs().sum())
+    return np.array([tot])
+
+
+def make_bert():
+    mod = refshim.load_bertmaxp()
+    for name, (cfg, N, P, L, qlen, wseed, iseed) in BERT_CONFIGS.items():
+        import transformers
+
+        vocab = transformers.BertConfig(**cfg).vocab_size
+        batch = synthetic.bert_batch(N, seqlen=L, qlen=qlen, vocab=vocab, seed=iseed, numpassages=P)
+        tb = _t(batch)
+        out = {k: v.astype(np.int32) for k, v in batch.items()}
+        out.update(reference_commit=np.array(refshim.REFERENCE_COMMIT), weight_seed=np.array(wseed), input_seed=np.array(iseed),
+                   shape=np.array([N, P, L, qlen]))
+        ext = refshim.FakeExtractor(None, numpassages=P, maxseqlen=L)
+        for agg in ["max", "first", "sum", "avg"]:
+            with refshim.patched_bert_from_pretrained(cfg, seed=wseed):
+                rr = mod.PTBERTMaxP(dict(pretrained="bert-base-uncased", aggregation=agg, hidden_dropout_prob=0.1),
+                                    provide={"extractor": ext})
+                model = rr.build_model().eval()
+            with torch.no_grad():
+                out[f"{agg}/scores"] = rr.test(tb).numpy()
+                if agg == "max":
+                    flat = lambda t: t.reshape(N * P, L)
+                    logits = model.bert(flat(tb["pos_bert_input"]), attention_mask=flat(tb["pos_mask"]),
+                                        token_type_ids=flat(tb["pos_seg"]))[0]
+                    out["logits"] = logits.numpy()
+                    out["weight_checksum"] = bert_weight_checksum(model.bert)
+                    out["config_json"] = np.array(model.bert.config.to_json_string())
+        np.savez_compressed(GOLDEN / f"bert_{name}.npz", **out)
+        print("bert", name, out["logits"][:3].tolist())
+
+
+TRAIN = dict(batch=32, itersize=512, niters=2, lr=1e-3, seed=4)
+
+
+def make_knrm_train():
+    """BASELINE.json configs[4]: reference PytorchTrainer.single_train_iteration (trainer/pytorch.py:76-122)
+    driving the reference KNRM with Adam + pair_hinge_loss for niters=2."""
+    ref = refshim.load_rerankers()
+    tr = refshim.load_trainer()
+    out = {}
+    for shape_name in ["full", "small"]:
+        B, Q, D, V, E, tseed, _ = SHAPES[shape_name]
+        table = synthetic.embedding_table(V, E, seed=tseed)
+        n_triples = TRAIN["itersize"] * TRAIN["niters"]
+        data = synthetic.train_triples(n_triples, Q, D, V, seed=TRAIN["seed"])
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        torch.manual_seed(100)
+        rr = ref.KNRM.KNRM(dict(gradkernels=True, scoretanh=False, singlefc=True, finetune=False), provide={"extractor": ext})
+        model = rr.build_model()
+        with torch.no_grad():
+            # untrained KNRM features are O(100); scale the combine layer so the hinge is active but not saturated
+            model.combine[0].weight.mul_(0.02)
+        init_state = {f"{shape_name}/init/{k[6:]}": v for k, v in _state_np(model).items()}
+        trainer = tr.PytorchTrainer.__new__(tr.PytorchTrainer)
+        trainer.config = dict(batch=TRAIN["batch"], evalbatch=0, niters=TRAIN["niters"], itersize=TRAIN["itersize"], gradacc=1,
+                              lr=TRAIN["lr"], softmaxloss=False, fastforward=False, validatefreq=1, multithread=False,
+                              boardname="default", warmupiters=0, decay=0.0, decayiters=3, decaytype=None, amp=None, seed=0)
+        trainer.build()
+        trainer.device = torch.device("cpu")
+        model.train()
+        trainer.optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=TRAIN["lr"])
+        trainer.amp_train_autocast = contextlib.nullcontext
+        trainer.scaler = None
+        trainer.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(trainer.optimizer, trainer.lr_multiplier)
+        trainer.loss = ref.common.pair_hinge_loss
+
+        def batches():
+            for s in range(0, n_triples, TRAIN["batch"]):
+                yield {k: torch.from_numpy(v[s:s + TRAIN["batch"]]) for k, v in data.items()}
+
+        it = batches()
+        losses = []
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for niter in range(TRAIN["niters"]):
+                losses.append(float(trainer.single_train_iteration(rr, it, niter)))
+        out.update(init_state)
+        out[f"{shape_name}/losses"] = np.array(losses)
+        out.update({f"{shape_name}/final/{k[6:]}": v for k, v in _state_np(model).items()})
+        out[f"{shape_name}/data_checksum"] = np.array([int(data["query"].sum()), int(data["posdoc"].sum()), int(data["negdoc"].sum())])
+        out[f"{shape_name}/table_checksum"] = table_checksum(table)
+        print("train", shape_name, losses)
+    out["train_config"] = np.array(repr(TRAIN))
+    np.savez_compressed(GOLDEN / "knrm_train.npz", **out)
+
+
+def make_losses():
+    ref = refshim.load_rerankers()
+    rng = np.random.default_rng(7)
+    pos, neg = rng.standard_normal(33).astype(np.float32) * 2, rng.standard_normal(33).astype(np.float32) * 2
+    tp, tn = torch.from_numpy(pos), torch.from_numpy(neg)
+    np.savez_compressed(GOLDEN / "losses.npz", pos=pos, neg=neg,
+                        hinge=ref.common.pair_hinge_loss([tp, tn]).numpy(), softmax=ref.common.pair_softmax_loss([tp, tn]).numpy())
+
+
+ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
+
+if __name__ == "__main__":
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    for name in (sys.argv[1:] or list(ALL)):
+        ALL[name]()
