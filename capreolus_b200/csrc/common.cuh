@@ -1,0 +1,67 @@
+// Shared device/host helpers for the capr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "capr_b200.h"
+
+namespace capr {
+
+// ---- host-side error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define CAPR_CHECK_CUDA(expr)                                 \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return capr::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define CAPR_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      capr::set_error(__VA_ARGS__);   \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+int sm_count();
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Token id (int64 in the reference layout) -> table row: ids <= 0 (pad, OOV) and ids >= V read the
+// all-zero <pad> row 0, which makes their cosine exactly 0 (capreolus/reranker/common.py:149-153,180).
+__device__ __forceinline__ int table_row(long long id, int V) { return (id > 0 && id < (long long)V) ? (int)id : 0; }
+// ids are compared for the OOV exact match (common.py:155-158,179); keep them as int (they are small).
+__device__ __forceinline__ int id_as_int(long long id) {
+  return id > 2147483647LL ? 2147483647 : (id < -2147483647LL ? -2147483647 : (int)id);
+}
+
+}  // namespace capr

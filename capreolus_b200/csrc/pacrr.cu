@@ -1,0 +1,223 @@
+// K3 -- fused PACRR scoring kernel.
+//
+//   PACRRConvMax2dModule.forward   capreolus/reranker/PACRR.py:73-82   pad -> Conv2d(1,F,n) -> ReLU -> max_f -> top-k_d
+//   PACRR_class.forward            capreolus/reranker/PACRR.py:43-54   n = mingram..maxgram, + softmax(idf), 3-layer MLP
+//   SimilarityMatrix               capreolus/reranker/common.py:143-182 (producer: simtile.cuh)
+//
+// The cosine tile stays in shared memory with a zero halo (the reference pads bottom/right with zeros,
+// PACRR.py:64), so each n x n window is n*n conflict-free LDS.  The F x n x n filter taps live in
+// __constant__ memory: the inner loop is FFMA with a constant-bank operand, no loads at all.
+// relu(max_f x_f) == max_f relu(x_f), so ReLU is applied once after the filter max.  Each lane keeps a
+// running top-k of its columns; lanes are merged with k rounds of warp max.  The reference's [B,F,Q,D]
+// conv output (2 MB per pair and n-gram) never exists.
+#include "simtile.cuh"
+
+namespace capr {
+
+constexpr int MAX_NGRAM = 5;     // largest conv window
+constexpr int MAX_FILTERS = 64;
+constexpr int MAX_KMAX = 8;
+constexpr int MAX_GRAMS = 5;     // number of n-gram modules
+constexpr int MAX_COMBINE = 128;
+constexpr int CONV_FLOATS = MAX_FILTERS * (1 + 4 + 9 + 16 + 25);
+
+__constant__ float c_conv_w[CONV_FLOATS];
+__constant__ float c_conv_b[MAX_GRAMS * MAX_FILTERS];
+
+struct PacrrArgs {
+  const long long* q;
+  const long long* d;
+  const float* idf;
+  int B, Q, D, V, pitch, mingram, maxgram, F, kmax, combine, nonlin;
+  int w_off[MAX_GRAMS];
+  const float* table;
+  const float *l1w, *l1b, *l2w, *l2b, *l3w, *l3b;
+  float* scores;
+  float* topk_out;
+};
+
+__device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ? fmaxf(x, 0.f) : (nonlin == 2 ? tanhf(x) : x); }
+
+// One n-gram module over the rows of this warp.  feat layout: [QT][qterm], this module writes columns
+// [col0, col0 + kmax).
+template <int N, int FT>
+__device__ __forceinline__ void ngram_pass(const SimTile& s, const PacrrArgs& a, int w_off, int b_off, int F, float* feat,
+                                           int qterm, int col0, int warp, int lane) {
+  constexpr int ROWS_PER_WARP = QT / (NT / 32);
+  for (int r = 0; r < ROWS_PER_WARP; ++r) {
+    const int qrow = warp * ROWS_PER_WARP + r;
+    if (qrow >= a.Q) continue;  // warp-uniform
+    float top[MAX_KMAX];
+#pragma unroll
+    for (int k = 0; k < MAX_KMAX; ++k) top[k] = -INFINITY;
+    for (int c = lane; c < a.D; c += 32) {
+      float win[N * N];
+#pragma unroll
+      for (int u = 0; u < N; ++u)
+#pragma unroll
+        for (int v = 0; v < N; ++v) win[u * N + v] = s.sim[(qrow + u) * SIM_PITCH + c + v];
+      float best = -INFINITY;
+      if (FT > 0) {
+#pragma unroll
+        for (int f = 0; f < FT; ++f) {
+          float x = c_conv_b[b_off + f];
+#pragma unroll
+          for (int t = 0; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
+          best = fmaxf(best, x);
+        }
+      } else {
+        for (int f = 0; f < F; ++f) {
+          float x = c_conv_b[b_off + f];
+#pragma unroll
+          for (int t = 0; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
+          best = fmaxf(best, x);
+        }
+      }
+      best = fmaxf(best, 0.f);  // ReLU (PACRR.py:78) commutes with the filter max (PACRR.py:79)
+      // insert into the lane-local descending top-k
+#pragma unroll
+      for (int k = 0; k < MAX_KMAX; ++k) {
+        if (k < a.kmax && best > top[k]) {
+          const float t = top[k];
+          top[k] = best;
+          best = t;
+        }
+      }
+    }
+    // merge the 32 lane-local lists: kmax rounds of (warp max, owner pops its head)
+    for (int k = 0; k < a.kmax; ++k) {
+      const float m = warp_max(top[0]);
+      const unsigned owners = __ballot_sync(0xffffffffu, top[0] == m);
+      if (lane == (__ffs(owners) - 1)) {
+#pragma unroll
+        for (int j = 0; j < MAX_KMAX - 1; ++j) top[j] = top[j + 1];
+        top[MAX_KMAX - 1] = -INFINITY;
+      }
+      if (lane == 0) feat[qrow * qterm + col0 + k] = m;
+    }
+  }
+}
+
+template <int FT>
+__device__ __forceinline__ void ngram_dispatch(int n, const SimTile& s, const PacrrArgs& a, int w_off, int b_off, float* feat,
+                                               int qterm, int col0, int warp, int lane) {
+  switch (n) {
+    case 1: ngram_pass<1, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+    case 2: ngram_pass<2, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+    case 3: ngram_pass<3, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+    case 4: ngram_pass<4, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+    default: ngram_pass<5, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) pacrr_kernel(const PacrrArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SimTile s = carve_sim_tile(smem_raw, a.pitch);
+  const int ngrams = a.maxgram - a.mingram + 1;
+  const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
+  float* feat = reinterpret_cast<float*>(smem_raw + sim_tile_bytes(a.pitch));  // [QT][qterm]
+  float* h1 = feat + QT * (MAX_GRAMS * MAX_KMAX + 1);                          // [MAX_COMBINE]
+  float* h2 = h1 + MAX_COMBINE;                                                // [MAX_COMBINE]
+  clear_sim_tile(s, tid);
+  __syncthreads();
+
+  for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x) {
+    build_sim_tile(s, a.table, a.pitch, a.V, a.q + (size_t)pair * a.Q, a.Q, a.d + (size_t)pair * a.D, 0, a.D, true, tid);
+    for (int g = 0; g < ngrams; ++g) {
+      const int n = a.mingram + g;
+      if (a.F == 32) ngram_dispatch<32>(n, s, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
+      else ngram_dispatch<0>(n, s, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
+    }
+    if (a.idf && warp == 0) {
+      // softmax over the query axis of the raw idf vector, pads included (PACRR.py:47-50)
+      const float v = lane < a.Q ? a.idf[(size_t)pair * a.Q + lane] : -INFINITY;
+      const float m = warp_max(v);
+      const float e = lane < a.Q ? expf(v - m) : 0.f;
+      const float den = warp_sum(e);
+      if (lane < a.Q) feat[lane * qterm + qterm - 1] = e / den;
+    }
+    __syncthreads();
+    if (a.topk_out) {
+      const int tk = ngrams * a.kmax;
+      for (int i = tid; i < a.Q * tk; i += NT) {
+        int r = i / tk, c = i - r * tk;
+        a.topk_out[((size_t)pair * a.Q + r) * tk + c] = feat[r * qterm + c];
+      }
+    }
+    // combine: Linear(Q*qterm, C) -> act -> Linear(C, C) -> act -> Linear(C, 1)   (PACRR.py:29-40,53)
+    const int in1 = a.Q * qterm;
+    for (int o = warp; o < a.combine; o += NT / 32) {
+      const float* w = a.l1w + (size_t)o * in1;
+      float p = 0.f;
+      for (int i = lane; i < in1; i += 32) p = fmaf(w[i], feat[i], p);  // feat is [Q][qterm] contiguous == flattened
+      p = warp_sum(p);
+      if (lane == 0) h1[o] = act(p + a.l1b[o], a.nonlin);
+    }
+    __syncthreads();
+    for (int o = warp; o < a.combine; o += NT / 32) {
+      const float* w = a.l2w + (size_t)o * a.combine;
+      float p = 0.f;
+      for (int i = lane; i < a.combine; i += 32) p = fmaf(w[i], h1[i], p);
+      p = warp_sum(p);
+      if (lane == 0) h2[o] = act(p + a.l2b[o], a.nonlin);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float p = 0.f;
+      for (int i = lane; i < a.combine; i += 32) p = fmaf(a.l3w[i], h2[i], p);
+      p = warp_sum(p);
+      if (lane == 0) a.scores[pair] = p + a.l3b[0];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace capr
+
+using namespace capr;
+
+extern "C" int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                                  const float* table, int V, int pitch, int mingram, int maxgram, int nfilters, int kmax,
+                                  const float* const* conv_w, const float* const* conv_b, const float* l1w,
+                                  const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
+                                  int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream) {
+  const char* fn = "capr_pacrr_forward";
+  CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d", fn, B, Q, D, V);
+  CAPR_REQUIRE(mingram >= 1 && maxgram >= mingram && nfilters > 0 && kmax > 0 && combine > 0, CAPR_ERR_BAD_SHAPE, "%s: bad config mingram=%d maxgram=%d nfilters=%d kmax=%d combine=%d", fn, mingram, maxgram, nfilters, kmax, combine);
+  CAPR_REQUIRE(nonlin >= 0 && nonlin <= 2, CAPR_ERR_BAD_SHAPE, "%s: nonlinearity must be none, relu or tanh", fn);
+  CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16", fn, pitch);
+  CAPR_REQUIRE(query && doc && table && conv_w && conv_b && l1w && l1b && l2w && l2b && l3w && l3b && scores, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
+  CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
+  CAPR_REQUIRE(D <= DT, CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d is not supported by the PACRR kernel yet", fn, D, DT);
+  CAPR_REQUIRE(D >= kmax, CAPR_ERR_BAD_SHAPE, "%s: kmax=%d exceeds maxdoclen=%d", fn, kmax, D);
+  CAPR_REQUIRE(pitch <= MAX_PITCH, CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d is not supported yet", fn, MAX_PITCH);
+  CAPR_REQUIRE(maxgram <= MAX_NGRAM && maxgram - mingram + 1 <= MAX_GRAMS, CAPR_ERR_UNSUPPORTED, "%s: maxgram=%d > %d is not supported", fn, maxgram, MAX_NGRAM);
+  CAPR_REQUIRE(nfilters <= MAX_FILTERS && kmax <= MAX_KMAX && combine <= MAX_COMBINE, CAPR_ERR_UNSUPPORTED, "%s: nfilters<=%d, kmax<=%d, combine<=%d", fn, MAX_FILTERS, MAX_KMAX, MAX_COMBINE);
+  if (B == 0) return CAPR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  PacrrArgs a{};
+  a.q = (const long long*)query; a.d = (const long long*)doc; a.idf = idf;
+  a.B = B; a.Q = Q; a.D = D; a.V = V; a.pitch = pitch; a.mingram = mingram; a.maxgram = maxgram; a.F = nfilters;
+  a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = table;
+  a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
+  // Stage the filter taps in constant memory (stream-ordered device-to-device copies; the constant bank
+  // is per device, so concurrent PACRR calls with different weights must share one stream).
+  int off = 0;
+  for (int g = 0; g <= maxgram - mingram; ++g) {
+    const int n = mingram + g;
+    CAPR_REQUIRE(conv_w[g] && conv_b[g], CAPR_ERR_BAD_POINTER, "%s: null conv weight %d", fn, g);
+    a.w_off[g] = off;
+    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_w, conv_w[g], sizeof(float) * nfilters * n * n, sizeof(float) * off, cudaMemcpyDeviceToDevice, st));
+    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * g * MAX_FILTERS, cudaMemcpyDeviceToDevice, st));
+    off += nfilters * n * n;
+  }
+  size_t smem = sim_tile_bytes(pitch) + (size_t)(QT * (MAX_GRAMS * MAX_KMAX + 1) + 2 * MAX_COMBINE) * sizeof(float);
+  CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  pacrr_kernel<<<B < sms ? B : sms, NT, smem, st>>>(a);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}

@@ -1,0 +1,116 @@
+/* capr_b200.h -- C ABI of the B200-native reranker scoring engine (libcapr_b200.so).
+ *
+ * This is the drop-in boundary of the repo: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the capreolus repo, commit
+ * 789288c).  The reference has no FFI of its own -- it is pure Python calling torch ops -- so the
+ * "binding a maintainer would add" is a ctypes stub; see INTEGRATION.md and capreolus_b200/_lib.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the parameter is documented as "host";
+ *   - token ids are int64, row-major [B,Q] / [B,D]:  id > 0 in-vocabulary, 0 = <pad>, < 0 = OOV
+ *     (capreolus/reranker/common.py:174, capreolus/extractor/embedtext.py:142-151);
+ *   - work is enqueued on `stream` (a cudaStream_t) and NOT synchronised; buffers are borrowed for
+ *     the duration of the enqueued work only;
+ *   - every function returns CAPR_OK or a negative capr_status; capr_last_error() gives the text for
+ *     the calling thread.  No function falls back to a CPU path.
+ */
+#ifndef CAPR_B200_H_
+#define CAPR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* capr_stream_t; /* cudaStream_t */
+
+typedef enum {
+  CAPR_OK = 0,
+  CAPR_ERR_BAD_SHAPE = -1,   /* a dimension is <= 0 or inconsistent */
+  CAPR_ERR_BAD_POINTER = -2, /* null or misaligned pointer */
+  CAPR_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented by the kernels (message says what) */
+  CAPR_ERR_CUDA = -4,        /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  CAPR_ERR_NO_DEVICE = -5    /* no sm_100 device visible */
+} capr_status;
+
+#define CAPR_ABI_VERSION 1
+int capr_abi_version(void);
+const char* capr_last_error(void);
+
+/* Number of SMs / compute capability major*10+minor of the current device (0 if none). */
+int capr_device_sm_count(void);
+int capr_device_arch(void);
+
+/* ---- embedding table --------------------------------------------------------------------------
+ * Replaces create_emb_layer + the two norm()/divide steps of SimilarityMatrix.cosine_similarity_matrix
+ * (capreolus/reranker/common.py:279-288, 161-165).  The kernels gather from a *prepared* table:
+ * row v = emb[v] / (||emb[v]||_2 + 1e-9), row pitch `capr_table_pitch(E)` floats (E rounded up to a
+ * multiple of 16, zero filled), so cos(q,d) is a plain dot product of two gathered rows.  Must be
+ * re-run whenever the embedding weights change (finetune=True). */
+int capr_table_pitch(int E);
+int capr_table_prepare(const float* emb /*[V,E]*/, int V, int E, float* table /*[V,pitch]*/, int pitch,
+                       capr_stream_t stream);
+
+/* ---- similarity matrix (debug / tests) ----------------------------------------------------------
+ * SimilarityMatrix.forward (capreolus/reranker/common.py:170-182): sim[B,Q,D] fp32. */
+int capr_simmat_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
+                        int pitch, float* sim /*[B,Q,D]*/, capr_stream_t stream);
+
+/* ---- KNRM -----------------------------------------------------------------------------------------
+ * KNRM_class.forward (capreolus/reranker/KNRM.py:39-55) with RbfKernelBank (common.py:224-250) fused:
+ * gather -> cosine tile -> K Gaussian kernels -> sum over doc -> masked log -> sum over query -> combine.
+ *   mu, sigma  [K]                     kernels.kernels.{k}.mu / .sigma
+ *   w1 [H,K], b1 [H]                   combine.0 ; H = 1 when hidden == 0 (singlefc=True)
+ *   w2 [1,hidden], b2 [1]              combine.2 (only when hidden > 0, i.e. singlefc=False)
+ *   flags                              CAPR_KNRM_SCORETANH = final tanh (scoretanh=True)
+ *   scores [B]       (nullable)        what KNRM.test / KNRM.score return per pair (KNRM.py:87-101)
+ *   feats  [B,K]     (nullable)        the log soft-TF features fed to `combine` (KNRM.py:53)
+ *   stats  [B,2,K]   (nullable)        backward statistics for d/dmu, d/dsigma
+ */
+#define CAPR_KNRM_SCORETANH 1
+int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
+                      int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1,
+                      int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
+                      float* stats, capr_stream_t stream);
+
+/* ---- DRMM -----------------------------------------------------------------------------------------
+ * DRMM_class.forward (capreolus/reranker/DRMM.py:101-116): _hist_map (41-81) + ffw + _term_gate (83-99).
+ *   idf [B,Q] fp32; bin_ub [nbins] = torch.linspace(-1,1,nbins+1)[1:] (device, the exact fp32 values)
+ *   hist_type: 0 = CH, 1 = NH, 2 = LCH;  gate_type: 0 = IDF (gate_w [1]), 1 = TV (gate_w [E], raw_emb [V,E])
+ *   ffw_w1 [nodes,nbins+1], ffw_b1 [nodes], ffw_w2 [nodes], ffw_b2 [1], out_w [1], out_b [1]
+ *   hist_out [B,Q,nbins+1] (nullable) is the transformed histogram _hist_map returns. */
+#define CAPR_DRMM_CH 0
+#define CAPR_DRMM_NH 1
+#define CAPR_DRMM_LCH 2
+#define CAPR_DRMM_GATE_IDF 0
+#define CAPR_DRMM_GATE_TV 1
+int capr_drmm_forward(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                      const float* table, int V, int pitch, const float* raw_emb, int E, int nbins,
+                      const float* bin_ub, int hist_type, int gate_type, const float* ffw_w1, const float* ffw_b1,
+                      int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w, const float* out_w,
+                      const float* out_b, float* scores, float* hist_out, capr_stream_t stream);
+
+/* ---- PACRR ----------------------------------------------------------------------------------------
+ * PACRR_class.forward (capreolus/reranker/PACRR.py:43-54) with PACRRConvMax2dModule (57-82) fused.
+ *   conv_w / conv_b: HOST arrays of (maxgram-mingram+1) device pointers, ngrams.{i}.conv.weight [F,1,n,n] / .bias [F]
+ *   idf [B,Q] or NULL (config idf=False);  nonlin: 0 none, 1 relu, 2 tanh
+ *   l1w [C, Q*(ngrams*kmax + (idf?1:0))], l1b [C], l2w [C,C], l2b [C], l3w [1,C], l3b [1]
+ *   topk_out [B,Q,ngrams*kmax] (nullable). */
+int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                       const float* table, int V, int pitch, int mingram, int maxgram, int nfilters, int kmax,
+                       const float* const* conv_w, const float* const* conv_b, const float* l1w, const float* l1b,
+                       const float* l2w, const float* l2b, const float* l3w, const float* l3b, int combine,
+                       int nonlin, float* scores, float* topk_out, capr_stream_t stream);
+
+/* ---- pairwise losses (tests / training loop) ------------------------------------------------------
+ * pair_hinge_loss (capreolus/reranker/common.py:7,101-103): loss[0] = mean(max(0, 1 - (pos - neg))),
+ * grad_pos/grad_neg [B] (nullable) = d loss / d score. */
+int capr_pair_hinge(const float* pos, const float* neg, int B, float* loss, float* grad_pos, float* grad_neg,
+                    capr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPR_B200_H_ */

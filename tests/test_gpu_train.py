@@ -1,0 +1,102 @@
+"""GPU: KNRM pairwise-hinge training (BASELINE.json configs[4]) -- gradients vs autograd through the oracle, and the
+niters=2 loss curve vs the golden produced by the reference PytorchTrainer + reference KNRM (oracle/make_goldens.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class Extractor:
+    def __init__(self, table, Q, D):
+        self.embeddings = table
+        self.config = {"maxqlen": Q, "maxdoclen": D}
+
+
+def test_hinge_loss_and_gradient():
+    from capreolus_b200.reranker.common import pair_hinge_loss
+
+    g = load_golden("losses")
+    pos = torch.from_numpy(g["pos"]).to(DEV).requires_grad_()
+    neg = torch.from_numpy(g["neg"]).to(DEV).requires_grad_()
+    loss = pair_hinge_loss([pos, neg])
+    np.testing.assert_allclose(loss.item(), g["hinge"], rtol=1e-6)
+    loss.backward()
+    p2 = torch.from_numpy(g["pos"]).requires_grad_()
+    n2 = torch.from_numpy(g["neg"]).requires_grad_()
+    torch.nn.MarginRankingLoss(margin=1)(p2, n2, torch.ones_like(p2)).backward()
+    assert torch.allclose(pos.grad.cpu(), p2.grad) and torch.allclose(neg.grad.cpu(), n2.grad)
+
+
+@pytest.mark.parametrize("shape", [(6, 8, 40, 500, 50), (4, 32, 512, 3000, 300)])
+def test_knrm_gradients_match_autograd_through_the_oracle(shape):
+    from capreolus_b200 import reranker as R, synthetic
+    from oracle import restated
+
+    B, Q, D, V, E = shape
+    table = synthetic.embedding_table(V, E, seed=3)
+    batch = synthetic.train_triples(B, Q, D, V, seed=5)
+    rr = R.KNRM(provide={"extractor": Extractor(table, Q, D)})
+    torch.manual_seed(1)
+    model = rr.build_model()
+    with torch.no_grad():
+        model.combine[0].weight.mul_(0.02)
+    # oracle: autograd through the restated forward, fp64-free, on CPU
+    state = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "embedding" not in k) for k, v in model.state_dict().items()}
+    cpu = {k: torch.from_numpy(v) for k, v in batch.items()}
+    ttable = torch.from_numpy(table)
+    pos = restated.knrm_forward(state, ttable, cpu["posdoc"], cpu["query"]).view(-1)
+    neg = restated.knrm_forward(state, ttable, cpu["negdoc"], cpu["query"]).view(-1)
+    loss_ref = restated.pair_hinge_loss(pos, neg)
+    loss_ref.backward()
+    # CUDA path
+    model.to(DEV).train()
+    from capreolus_b200.reranker.common import pair_hinge_loss
+
+    loss = pair_hinge_loss(rr.score({k: v.to(DEV) for k, v in cpu.items()}))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-4)
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        want = state[name].grad
+        assert p.grad is not None, name
+        scale = max(float(want.abs().max()), 1e-6)
+        assert float((p.grad.cpu() - want).abs().max()) <= 2e-3 * scale + 1e-6, (name, p.grad.cpu(), want)
+
+
+@pytest.mark.parametrize("shape_name,dims", [("small", (8, 40, 500, 50, 10)), ("full", (32, 512, 30000, 300, 0))])
+def test_knrm_loss_curve_matches_reference_trainer(shape_name, dims):
+    from capreolus_b200 import reranker as R, synthetic
+    from capreolus_b200.trainer import PairwiseTrainer
+
+    Q, D, V, E, tseed = dims
+    g = load_golden("knrm_train")
+    cfg = dict(batch=32, itersize=512, niters=2, lr=1e-3, seed=4)  # oracle/make_goldens.py TRAIN
+    table = synthetic.embedding_table(V, E, seed=tseed)
+    n_triples = cfg["itersize"] * cfg["niters"]
+    data = synthetic.train_triples(n_triples, Q, D, V, seed=cfg["seed"])
+    chk = np.array([int(data["query"].sum()), int(data["posdoc"].sum()), int(data["negdoc"].sum())])
+    assert np.array_equal(chk, g[f"{shape_name}/data_checksum"]), "synthetic TRAIN set differs from the one the golden was made with"
+    rr = R.KNRM(provide={"extractor": Extractor(table, Q, D)})
+    model = rr.build_model()
+    init = {k[len(f"{shape_name}/init/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"{shape_name}/init/")}
+    model.load_state_dict(init, strict=False)
+    trainer = PairwiseTrainer(batch=cfg["batch"], itersize=cfg["itersize"], lr=cfg["lr"], device=DEV)
+    trainer.prepare(rr)
+
+    def batches():
+        for s in range(0, n_triples, cfg["batch"]):
+            yield {k: torch.from_numpy(v[s:s + cfg["batch"]]) for k, v in data.items()}
+
+    it = batches()
+    losses = [float(trainer.single_train_iteration(rr, it, i)) for i in range(cfg["niters"])]
+    np.testing.assert_allclose(losses, g[f"{shape_name}/losses"], rtol=2e-3)
+    assert losses[1] < losses[0]
+    final = {k[len(f"{shape_name}/final/"):]: v for k, v in g.items() if k.startswith(f"{shape_name}/final/")}
+    got = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items() if k in final}
+    for k, want in final.items():
+        np.testing.assert_allclose(got[k], want, rtol=5e-3, atol=2e-4, err_msg=k)

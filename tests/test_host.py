@@ -1,0 +1,192 @@
+"""CPU: host-side logic -- the C-ABI library loads and exports every declared symbol, the drop-in modules keep the
+reference's API surface / checkpoint format, sharding arithmetic, and the world_size-2 gloo gather."""
+import os
+import pickle
+import re
+import socket
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_state, load_golden
+
+from capreolus_b200 import _lib, reranker as R, sharding, synthetic
+
+
+class Extractor:
+    def __init__(self, V=50, E=20, Q=4, D=12, seed=0):
+        self.embeddings = synthetic.embedding_table(V, E, seed=seed)
+        self.config = {"maxqlen": Q, "maxdoclen": D}
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    header = (ROOT / "include" / "capr_b200.h").read_text()
+    declared = set(re.findall(r"\b(capr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()  # raises if the .so is missing or lacks a symbol
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.capr_abi_version() == 1
+    assert lib.capr_table_pitch(300) == 304 and lib.capr_table_pitch(16) == 16 and lib.capr_table_pitch(1) == 16
+
+
+def test_abi_argument_validation_without_a_gpu():
+    lib = _lib.lib()
+    # argument checks run before any CUDA call, so they are testable on a CPU-only box
+    rc = lib.capr_table_prepare(None, 10, 8, None, 16, None)
+    assert rc == _lib.BAD_POINTER and b"null" in lib.capr_last_error()
+    rc = lib.capr_table_prepare(None, 0, 8, None, 16, None)
+    assert rc == _lib.BAD_SHAPE
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    rc = lib.capr_knrm_forward(8, 8, 4, 40, 16, 16, 10, 16, 8, 8, 11, 8, 8, 0, None, None, 0, 8, None, None, None)
+    assert rc == _lib.UNSUPPORTED and b"maxqlen" in lib.capr_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.NativeLibraryMissing, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_cpu_tensors_are_rejected_not_silently_scored():
+    rr = R.KNRM(provide={"extractor": Extractor()})
+    rr.build_model().eval()
+    batch = {"query": torch.ones(2, 4, dtype=torch.long), "posdoc": torch.ones(2, 12, dtype=torch.long), "query_idf": torch.zeros(2, 4)}
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        rr.test(batch)
+
+
+@pytest.mark.parametrize("cls,golden,variants", [
+    ("KNRM", "knrm_small", ["default", "twofc", "tanh"]),
+    ("DRMM", "drmm_small", ["default", "nh", "ch_tv"]),
+    ("PACRR", "pacrr_small", ["default", "noidf_tanh", "wide"]),
+])
+def test_state_dict_keys_and_shapes_match_the_reference(cls, golden, variants):
+    cfgs = {
+        "KNRM": {"default": {}, "twofc": {"singlefc": False}, "tanh": {"scoretanh": True}},
+        "DRMM": {"default": {}, "nh": {"histType": "NH"}, "ch_tv": {"nbins": 11, "nodes": 7, "histType": "CH", "gateType": "TV"}},
+        "PACRR": {"default": {}, "noidf_tanh": {"idf": False, "nonlinearity": "tanh"},
+                  "wide": {"mingram": 2, "nfilters": 16, "kmax": 3, "combine": 24, "nonlinearity": "none"}},
+    }[cls]
+    g = load_golden(golden)
+    B, Q, D, V, E = (int(x) for x in g["shape"])
+    for variant in variants:
+        ref_state = golden_state(g, variant)
+        model = getattr(R, cls)(cfgs[variant], provide={"extractor": Extractor(V, E, Q, D, seed=int(g["table_seed"]))}).build_model()
+        ours = model.state_dict()
+        assert set(ref_state) <= set(ours), set(ref_state) - set(ours)
+        assert set(ours) - set(ref_state) <= {"embedding.weight", "simmat.embedding.weight"}
+        for k, v in ref_state.items():
+            assert tuple(ours[k].shape) == tuple(v.shape), k
+        model.load_state_dict(ref_state, strict=False)
+
+
+def test_save_and_load_weights_use_the_reference_checkpoint_format(tmp_path):
+    rr = R.KNRM(provide={"extractor": Extractor()})
+    model = rr.build_model()
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3)
+    fn = tmp_path / "weights" / "dev.best"
+    rr.save_weights(fn, opt)
+    saved = pickle.load(open(fn, "rb"))
+    assert not any("embedding.weight" in k or "_nosave_" in k for k in saved)  # reranker/__init__.py:34
+    assert "kernels.kernels.10.sigma" in saved and "combine.0.weight" in saved
+    assert Path(fn.as_posix() + ".optimizer").exists()
+    with torch.no_grad():
+        model.combine[0].weight.zero_()
+    rr.load_weights(fn, opt)
+    assert torch.equal(model.combine[0].weight, saved["combine.0.weight"])
+    del saved["combine.0.bias"]
+    pickle.dump(saved, open(fn, "wb"))
+    with pytest.raises(RuntimeError, match="do not match"):
+        rr.load_weights(fn, opt)
+
+
+def test_config_handling_and_registry():
+    rr = R.Reranker.create("DRMM", {"nbins": 11}, provide={"extractor": Extractor()})
+    assert isinstance(rr, R.DRMM) and rr.config["nbins"] == 11 and rr.config["histType"] == "LCH"
+    with pytest.raises(ValueError):
+        R.KNRM({"nosuchoption": 1}, provide={"extractor": Extractor()})
+    with pytest.raises(ValueError):
+        R.Reranker.create("nosuchmodel")
+    with pytest.raises(ValueError, match="gateType"):
+        R.DRMM({"gateType": "XX"}, provide={"extractor": Extractor()}).build_model()
+    m1 = rr.build_model()
+    assert rr.build_model() is m1  # build_model is idempotent (DRMM.py:135-139)
+
+
+def test_synthetic_inputs_are_deterministic_and_well_formed():
+    a, b = synthetic.parity_batch(16, 8, 40, 500, seed=3), synthetic.parity_batch(16, 8, 40, 500, seed=3)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert a["query"].dtype == np.int64 and a["posdoc"].shape == (16, 40) and a["query_idf"].dtype == np.float32
+    assert (a["query"] < 0).any() and (a["query"] == 0).any() and (a["query"][3] == 0).all()
+    assert not (synthetic.parity_batch(16, 8, 40, 500, seed=3, oov=False)["query"] < 0).any()
+    t = synthetic.embedding_table(100, 8, seed=1)
+    assert (t[0] == 0).all() and t.dtype == np.float32
+    bb = synthetic.bert_batch(3, seqlen=64, qlen=8, vocab=2000, seed=1, numpassages=2)
+    ids, mask, seg = bb["pos_bert_input"], bb["pos_mask"], bb["pos_seg"]
+    assert ids.shape == (3, 2, 64) and (ids[:, :, 0] == synthetic.CLS).all() and (ids[:, :, 9] == synthetic.SEP).all()
+    assert (seg[:, :, :10] == 0).all() and (seg[:, :, 10:] == 1).all()  # segment ids stay 1 through the padding
+    assert ((ids != 0) == (mask == 1)).all()
+
+
+def test_shard_bounds_partition_exactly():
+    for n in (0, 1, 7, 64, 100_000, 1_000_003):
+        for world in (1, 2, 3, 4, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = sharding.shard_bounds(n, r, world)
+                assert 0 <= lo <= hi <= n
+                cover.extend(range(lo, hi)) if n < 1000 else cover.append((lo, hi))
+            if n < 1000:
+                assert cover == list(range(n))
+            else:
+                assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
+class _FakeReranker:
+    """Deterministic per-pair scorer on CPU tensors (stands in for the CUDA path in the gloo test)."""
+
+    def test(self, batch):
+        return (batch["query"].float().sum(dim=1) * 0.5 + batch["posdoc"].float().sum(dim=1) * 0.25).view(-1)
+
+
+def _gloo_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        batch = {"query": torch.from_numpy(rng.integers(0, 100, (n, 4))), "posdoc": torch.from_numpy(rng.integers(0, 100, (n, 9))),
+                 "qid": [str(i) for i in range(n)]}
+        got = sharding.ShardedScorer(_FakeReranker()).test(batch)
+        want = _FakeReranker().test(batch)
+        q.put((rank, bool(torch.equal(got, want)), tuple(got.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 1])
+def test_sharded_scoring_with_gloo_world_size_2(n):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in results) == [0, 1]
+    assert all(ok and shape == (n,) for _, ok, shape in results), results
