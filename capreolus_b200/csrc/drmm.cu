@@ -11,6 +11,9 @@
 // the host passes in, i.e. torch.linspace(-1,1,nbins+1)[1:]), which is the same partition.  Quirks kept:
 // padded doc columns fall in no bin (DRMM.py:59); padded query rows still histogram and are removed only
 // by the -1e7 gate mask (DRMM.py:89); the last slot counts 0.999 < s < 1.001 and overlaps bin nbins-1.
+// Identical tokens: the fp32 reference puts them in the last regular bin or not depending on the rounding of
+// a.a/(|a|+1e-9)^2 (a coin flip per token); we follow the exact-arithmetic value (< 1.0 -> in the bin), which is what
+// the reference computes when its cosines are evaluated in fp64 (tests/test_oracle.py pins this).
 // Counting is integer work: __match_any_sync groups the lanes of a warp by bin and the group leader adds
 // the group's size to a per-row shared-memory counter (no atomics, deterministic).
 #include "simtile.cuh"
@@ -65,6 +68,10 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
           b = max(0, min(b, a.nbins));
           while (b < a.nbins && !(v < ub[b])) ++b;
           while (b > 0 && v < ub[b - 1]) --b;
+          // identical in-vocabulary tokens are stored as exactly 1.0f (simtile.cuh); their exact-arithmetic cosine
+          // 1 - 2e-9/|a| is < 1.0, i.e. inside the last regular bin [ub[nbins-2], 1.0) as well as the exact slot
+          const int qi = s.qid[qrow];
+          if (real && v == 1.0f && qi > 0 && qi == s.did[c]) b = a.nbins - 1;
           if (!real) b = a.nbins + 1;  // sentinel group, never stored
           const unsigned peers = __match_any_sync(0xffffffffu, b);
           if (b < a.nbins && lane == (__ffs(peers) - 1)) c_row[b] += __popc(peers);
@@ -145,7 +152,7 @@ extern "C" int capr_drmm_forward(const int64_t* query, const int64_t* doc, const
   const char* fn = "capr_drmm_forward";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && nodes > 0 && nbins > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d nodes=%d nbins=%d", fn, B, Q, D, V, nodes, nbins);
   CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16", fn, pitch);
-  CAPR_REQUIRE(query && doc && table && bin_ub && ffw_w1 && ffw_b1 && ffw_w2 && ffw_b2 && gate_w && out_w && out_b && scores, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(B == 0 || (query && doc && table && bin_ub && ffw_w1 && ffw_b1 && ffw_w2 && ffw_b2 && gate_w && out_w && out_b && scores), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
   CAPR_REQUIRE(hist_type >= 0 && hist_type <= 2, CAPR_ERR_BAD_SHAPE, "%s: histType should be CH, NH or LCH", fn);
   CAPR_REQUIRE(gate_type == 0 || gate_type == 1, CAPR_ERR_BAD_SHAPE, "%s: gateType should be IDF or TV", fn);

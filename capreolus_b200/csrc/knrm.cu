@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) simmat_kernel(const long long* q, const
 static int check_common(const char* fn, const void* q, const void* d, int B, int Q, int D, const float* table, int V, int pitch) {
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d", fn, B, Q, D, V);
   CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16 (capr_table_pitch)", fn, pitch);
-  CAPR_REQUIRE(q && d && table, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(B == 0 || (q && d && table), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
   CAPR_REQUIRE(pitch <= MAX_PITCH, CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d is not supported by the fused kernels yet", fn, MAX_PITCH);
@@ -224,7 +224,7 @@ int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, in
   CAPR_REQUIRE(K > 0 && hidden >= 0, CAPR_ERR_BAD_SHAPE, "capr_knrm_forward: K=%d hidden=%d", K, hidden);
   CAPR_REQUIRE(K <= 32, CAPR_ERR_UNSUPPORTED, "capr_knrm_forward: more than 32 kernels (K=%d) is not supported", K);
   CAPR_REQUIRE(mu && sigma, CAPR_ERR_BAD_POINTER, "capr_knrm_forward: null mu/sigma");
-  CAPR_REQUIRE(scores || feats || stats, CAPR_ERR_BAD_POINTER, "capr_knrm_forward: no output requested");
+  CAPR_REQUIRE(B == 0 || scores || feats || stats, CAPR_ERR_BAD_POINTER, "capr_knrm_forward: no output requested");
   if (scores) {
     CAPR_REQUIRE(w1 && b1, CAPR_ERR_BAD_POINTER, "capr_knrm_forward: scores requested without combine weights");
     CAPR_REQUIRE(hidden == 0 || (w2 && b2), CAPR_ERR_BAD_POINTER, "capr_knrm_forward: hidden=%d needs w2/b2", hidden);

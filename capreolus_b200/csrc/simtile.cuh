@@ -152,6 +152,12 @@ __device__ __forceinline__ void sim_tile_gemm(const SimTile& s, const float* __r
 }
 
 // Store the accumulators into s.sim, adding the OOV exact match (common.py:155-158,179-181).
+//
+// Identical in-vocabulary tokens: the reference's fp32 self-cosine a.a / (|a|+1e-9)^2 is 1 +- 1 ulp with the sign
+// set by rounding (measured on the N(0,1) table: 43 % below, 15 % equal, 43 % above 1.0), while its exact value is
+// 1 - 2e-9/|a|.  We store exactly 1.0f for such cells (when the row is not a zero vector), so that every engine and
+// every summation order agrees on them; DRMM, whose last regular bin tests `s < 1.0`, bins these cells by their
+// exact-arithmetic value (drmm.cu).  See DESIGN.md "Exact matches".
 __device__ __forceinline__ void store_sim_tile(const SimTile& s, int tid, const float (&acc)[8][8]) {
   const int ty = tid >> 6, tx = tid & 63;
 #pragma unroll
@@ -161,7 +167,10 @@ __device__ __forceinline__ void store_sim_tile(const SimTile& s, int tid, const 
     for (int j = 0; j < 8; ++j) {
       const int col = tx + 64 * j;
       float v = acc[i][j];
-      if (qi < 0 && qi == s.did[col]) v += 1.0f;
+      if (qi == s.did[col]) {
+        if (qi < 0) v += 1.0f;
+        else if (v > 0.5f) v = 1.0f;
+      }
       s.sim[(ty * 8 + i) * SIM_PITCH + col] = v;
     }
   }

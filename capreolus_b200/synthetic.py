@@ -36,12 +36,14 @@ def zipf_ids(rng: np.random.Generator, shape, vocab: int = VOCAB) -> np.ndarray:
 
 
 def parity_batch(batch: int = 64, qlen: int = MAXQLEN, dlen: int = MAXDOCLEN, vocab: int = VOCAB, seed: int = 1,
-                 oov: bool = True) -> dict:
+                 oov: bool = True, disjoint: bool = False) -> dict:
     """The PARITY set: ragged lengths right-padded with 0, shared OOV (negative) ids, one all-pad query.
 
     Returns numpy arrays ``query [B,Q] int64``, ``posdoc``/``negdoc [B,D] int64``, ``query_idf [B,Q] f32``.
     ``oov=False`` leaves out the negative ids (the reference DRMM indexes the table with the raw query ids,
-    ``reranker/DRMM.py:109``, and raises IndexError on them).
+    ``reranker/DRMM.py:109``, and raises IndexError on them).  ``disjoint=True`` draws query terms from the even
+    and document terms from the odd ids, so that no in-vocabulary exact match occurs (the reference's fp32 result for
+    identical tokens is rounding noise -- DESIGN.md "Exact matches" -- and some checks need inputs free of it).
     """
     rng = np.random.default_rng(seed)
     query = zipf_ids(rng, (batch, qlen), vocab)
@@ -52,8 +54,13 @@ def parity_batch(batch: int = 64, qlen: int = MAXQLEN, dlen: int = MAXDOCLEN, vo
         qn[0], dn[0][0], dn[1][0] = qlen, dlen, dlen  # one completely full pair
         qn[1] = 1  # a one-term query
         dn[0][2] = min(16, dlen)  # shortest document
+    if disjoint:
+        half = (vocab - 1) // 2
+        query = 2 * np.minimum(zipf_ids(rng, (batch, qlen), half + 1), half)  # even ids in [2, vocab)
+        docs = [2 * np.minimum(zipf_ids(rng, (batch, dlen), half + 1), half) - 1 for _ in range(2)]  # odd ids in [1, vocab)
+        oov = False
     # every query term also occurs somewhere in its documents (soft-TF needs exact matches to be exercised)
-    for b in range(batch):
+    for b in range(batch if not disjoint else 0):
         for doc in docs:
             pos = rng.integers(0, dlen, size=qlen // 4 + 1)
             doc[b, pos] = query[b, rng.integers(0, qlen, size=pos.shape[0])]
@@ -87,12 +94,14 @@ def throughput_batch(n: int, qlen: int = MAXQLEN, dlen: int = MAXDOCLEN, vocab: 
     }
 
 
-def train_triples(n: int, qlen: int = MAXQLEN, dlen: int = MAXDOCLEN, vocab: int = VOCAB, seed: int = 4) -> dict:
-    """The TRAIN set: (query, posdoc, negdoc) triples; posdoc shares more terms with the query than negdoc."""
+def train_triples(n: int, qlen: int = MAXQLEN, dlen: int = MAXDOCLEN, vocab: int = VOCAB, seed: int = 4,
+                  disjoint: bool = False) -> dict:
+    """The TRAIN set: (query, posdoc, negdoc) triples; posdoc shares more terms with the query than negdoc
+    (``disjoint=True``: no shared terms at all, see ``parity_batch``)."""
     rng = np.random.default_rng(seed)
-    out = parity_batch(n, qlen, dlen, vocab, seed=seed)
+    out = parity_batch(n, qlen, dlen, vocab, seed=seed, disjoint=disjoint)
     pos = out["posdoc"]
-    for b in range(n):
+    for b in range(n if not disjoint else 0):
         real_q = out["query"][b][out["query"][b] > 0]
         nd = int((pos[b] != 0).sum())
         if real_q.size and nd:

@@ -103,6 +103,8 @@ def make_drmm():
         table, batch = _inputs(shape_name, oov=False)  # DRMM.py:109 cannot take negative (OOV) query ids
         B, Q, D, V, E, *_ = SHAPES[shape_name]
         tb = _t(batch)
+        dj = synthetic.parity_batch(B, Q, D, V, seed=SHAPES[shape_name][6] + 100, disjoint=True)
+        tdj = _t(dj)
         out = _common(shape_name, table, batch)
         ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
         for variant, cfg in {
@@ -123,9 +125,24 @@ def make_drmm():
                 if variant == "default":
                     d_mask = (tb["posdoc"] != 0).float()
                     out["hist"] = model._hist_map(tb["query"], tb["posdoc"], d_mask).numpy()
+                # inputs free of in-vocabulary exact matches: the fp32 reference is trustworthy there
+                pos_dj, neg_dj = rr.score(tdj)
+                # the same reference module, but with its SimilarityMatrix (reference class) holding a float64 copy of
+                # the table: cosines in exact arithmetic, everything after the integer counts unchanged (fp32)
+                emb64 = torch.nn.Embedding.from_pretrained(torch.from_numpy(table).double())
+                fp32_simmat, model.simmat = model.simmat, ref.common.SimilarityMatrix(emb64)
+                pos64, neg64 = rr.score(tb)
+                if variant == "default":
+                    out["hist64"] = model._hist_map(tb["query"], tb["posdoc"], d_mask).numpy()
+                model.simmat = fp32_simmat
             out[f"{variant}/pos"] = pos.numpy()
             out[f"{variant}/neg"] = neg.numpy()
+            out[f"{variant}/pos64"] = pos64.numpy()
+            out[f"{variant}/neg64"] = neg64.numpy()
+            out[f"{variant}/disjoint_pos"] = pos_dj.numpy()
+            out[f"{variant}/disjoint_neg"] = neg_dj.numpy()
             out.update({f"{variant}/{k}": v for k, v in _state_np(model).items()})
+        out.update({f"disjoint/{k}": (v.astype(np.int32) if v.dtype == np.int64 else v) for k, v in dj.items()})
         np.savez_compressed(GOLDEN / f"drmm_{shape_name}.npz", **out)
         print("drmm", shape_name, out["default/pos"][:4])
 
@@ -216,14 +233,19 @@ def make_knrm_train():
     ref = refshim.load_rerankers()
     tr = refshim.load_trainer()
     out = {}
-    for shape_name in ["full", "small"]:
+    # Two well-posed settings (DESIGN.md "Exact matches": with gradkernels=True AND identical tokens in query and doc the
+    # reference's own d/dmu, d/dsigma of the sigma=0.001 kernel is fp32 rounding noise that Adam turns into +-lr steps):
+    #   frozen   : zipf triples with exact matches, gradkernels=False (only `combine` trains)
+    #   disjoint : triples without shared terms, gradkernels=True (all 24 scalars train)
+    for shape_name, setting in [(s_, t_) for s_ in ["full", "small"] for t_ in ["frozen", "disjoint"]]:
         B, Q, D, V, E, tseed, _ = SHAPES[shape_name]
         table = synthetic.embedding_table(V, E, seed=tseed)
         n_triples = TRAIN["itersize"] * TRAIN["niters"]
-        data = synthetic.train_triples(n_triples, Q, D, V, seed=TRAIN["seed"])
+        data = synthetic.train_triples(n_triples, Q, D, V, seed=TRAIN["seed"], disjoint=setting == "disjoint")
         ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
         torch.manual_seed(100)
-        rr = ref.KNRM.KNRM(dict(gradkernels=True, scoretanh=False, singlefc=True, finetune=False), provide={"extractor": ext})
+        rr = ref.KNRM.KNRM(dict(gradkernels=setting == "disjoint", scoretanh=False, singlefc=True, finetune=False), provide={"extractor": ext})
+        shape_name = f"{shape_name}_{setting}"
         model = rr.build_model()
         with torch.no_grad():
             # untrained KNRM features are O(100); scale the combine layer so the hinge is active but not saturated

@@ -37,15 +37,22 @@ def _zero_pads(sim, q, d):
     return torch.where((d == 0)[:, None, :], torch.zeros_like(sim), sim)
 
 
-def similarity_matrix(table: torch.Tensor, q: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+def similarity_matrix(table: torch.Tensor, q: torch.Tensor, d: torch.Tensor, exact_cosines: bool = False) -> torch.Tensor:
     """reranker/common.py:170-182.  ``q [B,Q]``, ``d [B,D]`` int64 -> ``[B,Q,D]`` fp32.
 
     ids > 0 in-vocab, 0 pad, < 0 OOV (l.174).  Exact-match part: ids clamped to <= 0 so only identical
     negative ids match (l.155-158,179).  Cosine part: ids clamped to >= 0; the raw dot product is divided
     by the product of (norm + 1e-9) (l.160-167,180).
+
+    ``exact_cosines=True`` evaluates the same expression with a float64 copy of the table and returns float64
+    ("the reference in exact arithmetic").  The fp32 self-cosine of a token, a.a / (|a|+1e-9)^2, lands on either
+    side of 1.0 by rounding; consumers that threshold at 1.0 (DRMM's last bin, ``DRMM.py:63-65``) or differentiate a
+    sigma=0.001 kernel at mu=1.0 (KNRM) amplify that noise to O(1) -- see DESIGN.md "Exact matches".
     """
+    if exact_cosines:
+        table = table.double()
     qn, dn = q.clamp(max=0), d.clamp(max=0)
-    exact = _zero_pads((qn[:, :, None] == dn[:, None, :]).float(), qn, dn)
+    exact = _zero_pads((qn[:, :, None] == dn[:, None, :]).to(table.dtype), qn, dn)
     qp, dp = q.clamp(min=0), d.clamp(min=0)
     a, b = F.embedding(qp, table), F.embedding(dp, table)
     a_den = a.norm(p=2, dim=2)[:, :, None] + 1e-9
@@ -109,7 +116,7 @@ def drmm_histogram(sim: torch.Tensor, doc: torch.Tensor, nbins=29, hist_type="LC
     Padded doc columns are pushed to +1e7 (l.59); count-below per upper bound ``linspace(-1,1,nbins+1)[1:]``
     (l.63-65); last slot = #(0.999 < s < 1.001) (l.66); slots nbins-1..1 are differenced (l.68-69);
     +1 (l.71); then NH / LCH / CH."""
-    d_mask = (doc != 0).float()
+    d_mask = (doc != 0).to(sim.dtype)
     s = sim + (1 - d_mask[:, None, :]) * 1e7
     hist = torch.zeros(s.shape[0], s.shape[1], nbins + 1, dtype=torch.float)
     bounds = torch.linspace(-1, 1, nbins + 1)[1:]
@@ -128,11 +135,14 @@ def drmm_histogram(sim: torch.Tensor, doc: torch.Tensor, nbins=29, hist_type="LC
     return hist
 
 
-def drmm_forward(state: dict, table, doc, query, query_idf, nbins=29, hist_type="LCH", gate_type="IDF") -> torch.Tensor:
-    """``DRMM_class.forward(sentence, query_sentence, query_idf)`` (reranker/DRMM.py:101-116) -> ``[B,1]``."""
+def drmm_forward(state: dict, table, doc, query, query_idf, nbins=29, hist_type="LCH", gate_type="IDF",
+                 exact_cosines: bool = False) -> torch.Tensor:
+    """``DRMM_class.forward(sentence, query_sentence, query_idf)`` (reranker/DRMM.py:101-116) -> ``[B,1]``.
+
+    ``exact_cosines``: bin float64 cosines (everything downstream of the integer counts stays fp32)."""
     B, Q = query.shape
     q_mask = (query != 0).float()
-    hist = drmm_histogram(similarity_matrix(table, query, doc), doc, nbins, hist_type)
+    hist = drmm_histogram(similarity_matrix(table, query, doc, exact_cosines), doc, nbins, hist_type)
     z = torch.tanh(F.linear(hist, state["ffw.0.weight"], state["ffw.0.bias"]))
     z = torch.tanh(F.linear(z, state["ffw.2.weight"], state["ffw.2.bias"])).reshape(B, Q)  # l.106
     neg = (1 - q_mask) * -1e7  # l.89

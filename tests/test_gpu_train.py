@@ -31,14 +31,18 @@ def test_hinge_loss_and_gradient():
     assert torch.allclose(pos.grad.cpu(), p2.grad) and torch.allclose(neg.grad.cpu(), n2.grad)
 
 
+@pytest.mark.parametrize("disjoint", [False, True])
 @pytest.mark.parametrize("shape", [(6, 8, 40, 500, 50), (4, 32, 512, 3000, 300)])
-def test_knrm_gradients_match_autograd_through_the_oracle(shape):
+def test_knrm_gradients_match_autograd_through_the_oracle(shape, disjoint):
+    """With exact matches present, d/dmu and d/dsigma of the sigma=0.001, mu=1.0 kernel are rounding noise IN THE
+    REFERENCE (fp32 autograd +8.0e-4 vs fp64 -2.2e-6 on the same batch, DESIGN.md 'Exact matches'), so that kernel's
+    two scalars are compared only on inputs without shared terms."""
     from capreolus_b200 import reranker as R, synthetic
     from oracle import restated
 
     B, Q, D, V, E = shape
     table = synthetic.embedding_table(V, E, seed=3)
-    batch = synthetic.train_triples(B, Q, D, V, seed=5)
+    batch = synthetic.train_triples(B, Q, D, V, seed=5, disjoint=disjoint)
     rr = R.KNRM(provide={"extractor": Extractor(table, Q, D)})
     torch.manual_seed(1)
     model = rr.build_model()
@@ -60,7 +64,7 @@ def test_knrm_gradients_match_autograd_through_the_oracle(shape):
     loss.backward()
     np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-4)
     for name, p in model.named_parameters():
-        if not p.requires_grad:
+        if not p.requires_grad or (not disjoint and name.startswith("kernels.kernels.10.")):
             continue
         want = state[name].grad
         assert p.grad is not None, name
@@ -68,20 +72,24 @@ def test_knrm_gradients_match_autograd_through_the_oracle(shape):
         assert float((p.grad.cpu() - want).abs().max()) <= 2e-3 * scale + 1e-6, (name, p.grad.cpu(), want)
 
 
-@pytest.mark.parametrize("shape_name,dims", [("small", (8, 40, 500, 50, 10)), ("full", (32, 512, 30000, 300, 0))])
-def test_knrm_loss_curve_matches_reference_trainer(shape_name, dims):
+@pytest.mark.parametrize("setting", ["frozen", "disjoint"])
+@pytest.mark.parametrize("shape,dims", [("small", (8, 40, 500, 50, 10)), ("full", (32, 512, 30000, 300, 0))])
+def test_knrm_loss_curve_matches_reference_trainer(shape, dims, setting):
+    """niters=2 of the reference PytorchTrainer + reference KNRM (golden) vs the same loop on the CUDA path.
+    frozen: zipf triples, gradkernels=False; disjoint: no shared terms, gradkernels=True (see oracle/make_goldens.py)."""
     from capreolus_b200 import reranker as R, synthetic
     from capreolus_b200.trainer import PairwiseTrainer
 
     Q, D, V, E, tseed = dims
+    shape_name = f"{shape}_{setting}"
     g = load_golden("knrm_train")
     cfg = dict(batch=32, itersize=512, niters=2, lr=1e-3, seed=4)  # oracle/make_goldens.py TRAIN
     table = synthetic.embedding_table(V, E, seed=tseed)
     n_triples = cfg["itersize"] * cfg["niters"]
-    data = synthetic.train_triples(n_triples, Q, D, V, seed=cfg["seed"])
+    data = synthetic.train_triples(n_triples, Q, D, V, seed=cfg["seed"], disjoint=setting == "disjoint")
     chk = np.array([int(data["query"].sum()), int(data["posdoc"].sum()), int(data["negdoc"].sum())])
     assert np.array_equal(chk, g[f"{shape_name}/data_checksum"]), "synthetic TRAIN set differs from the one the golden was made with"
-    rr = R.KNRM(provide={"extractor": Extractor(table, Q, D)})
+    rr = R.KNRM({"gradkernels": setting == "disjoint"}, provide={"extractor": Extractor(table, Q, D)})
     model = rr.build_model()
     init = {k[len(f"{shape_name}/init/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"{shape_name}/init/")}
     model.load_state_dict(init, strict=False)
@@ -95,7 +103,8 @@ def test_knrm_loss_curve_matches_reference_trainer(shape_name, dims):
     it = batches()
     losses = [float(trainer.single_train_iteration(rr, it, i)) for i in range(cfg["niters"])]
     np.testing.assert_allclose(losses, g[f"{shape_name}/losses"], rtol=2e-3)
-    assert losses[1] < losses[0]
+    if setting == "frozen":
+        assert losses[1] < losses[0]
     final = {k[len(f"{shape_name}/final/"):]: v for k, v in g.items() if k.startswith(f"{shape_name}/final/")}
     got = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items() if k in final}
     for k, want in final.items():

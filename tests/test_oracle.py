@@ -56,11 +56,38 @@ def test_drmm_scores(shape, variant, kw):
     for side, doc in (("pos", "posdoc"), ("neg", "negdoc")):
         got = restated.drmm_forward(st, table, tb[doc], tb["query"], tb["query_idf"], **kw).view(-1).numpy()
         assert rel_err(got, g[f"{variant}/{side}"]) < 1e-4
+        # the reference with float64 cosines (its SimilarityMatrix holding a double table) == the exact_cosines oracle
+        got = restated.drmm_forward(st, table, tb[doc], tb["query"], tb["query_idf"], exact_cosines=True, **kw).view(-1).numpy()
+        assert rel_err(got, g[f"{variant}/{side}64"]) < 1e-5
+    dj = {k: torch.from_numpy(g[f"disjoint/{k}"].astype(np.int64) if g[f"disjoint/{k}"].dtype == np.int32 else g[f"disjoint/{k}"]) for k in ("query", "posdoc", "negdoc", "query_idf")}
+    got = restated.drmm_forward(st, table, dj["posdoc"], dj["query"], dj["query_idf"], **kw).view(-1).numpy()
+    assert rel_err(got, g[f"{variant}/disjoint_pos"]) < 1e-4
     if variant == "default":
         sim = restated.similarity_matrix(table, tb["query"], tb["posdoc"])
         hist = restated.drmm_histogram(sim, tb["posdoc"], 29, "LCH").numpy()
         # counts are discontinuous in the cosine: allow a handful of bin-edge flips
         assert (np.abs(hist - g["hist"]) > 1e-5).mean() < 1e-4
+        sim64 = restated.similarity_matrix(table, tb["query"], tb["posdoc"], exact_cosines=True)
+        assert np.array_equal(restated.drmm_histogram(sim64, tb["posdoc"], 29, "LCH").numpy(), g["hist64"])
+
+
+def test_reference_fp32_self_cosine_is_rounding_noise():
+    """Documents DESIGN.md 'Exact matches': for identical tokens the reference's fp32 cosine lands on either side of 1.0,
+    so (a) DRMM's last regular bin (`s < 1.0`, DRMM.py:63-65) is a coin flip per token and fp32 vs fp64 reference scores
+    differ by far more than 1e-3, and (b) in exact arithmetic every exact match is inside that bin."""
+    g = load_golden("drmm_full")
+    table = torch.from_numpy(golden_table(g))
+    ids = torch.arange(1, 2049).reshape(64, 32)
+    sim = restated.similarity_matrix(table, ids, ids)
+    diag = torch.diagonal(sim, dim1=1, dim2=2).reshape(-1)
+    below, above = float((diag < 1).float().mean()), float((diag >= 1).float().mean())
+    assert 0.2 < below < 0.8 and 0.2 < above < 0.8, (below, above)
+    diag64 = torch.diagonal(restated.similarity_matrix(table, ids, ids, exact_cosines=True), dim1=1, dim2=2)
+    assert bool((diag64 < 1).all()) and bool((diag64 > 0.999999).all())
+    assert rel_err(g["default/pos"], g["default/pos64"]) > 1e-2  # fp32 reference vs itself with exact cosines
+    # exact-arithmetic histogram: every exact match (last slot) is also in the last regular bin
+    c64 = np.rint(np.exp(g["hist64"])) - 1
+    assert np.all(c64[:, :, 28] >= c64[:, :, 29])
 
 
 @pytest.mark.parametrize("shape", SHAPES)
