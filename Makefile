@@ -16,7 +16,7 @@ $(BUILDDIR)/%.o: $(SRCDIR)/%.cu $(wildcard $(SRCDIR)/*.cuh) include/capr_b200.h
 	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcuda
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) 
 
 clean:
 	rm -rf build $(LIB)

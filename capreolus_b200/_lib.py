@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
 from pathlib import Path
 
 LIB_NAME = "libcapr_b200.so"
@@ -19,6 +19,16 @@ CAPR_OK, BAD_SHAPE, BAD_POINTER, UNSUPPORTED, CUDA_ERROR, NO_DEVICE = 0, -1, -2,
 _lib = None
 
 _f32p, _i64p = c_void_p, c_void_p  # device pointers travel as plain addresses (tensor.data_ptr())
+
+
+class BertConfigStruct(Structure):
+    """``capr_bert_config`` of include/capr_b200.h"""
+
+    _fields_ = [("hidden", c_int), ("layers", c_int), ("heads", c_int), ("intermediate", c_int), ("vocab", c_int), ("max_pos", c_int),
+                ("type_vocab", c_int), ("n_labels", c_int), ("ln_eps", c_float)]
+
+
+BERT_BF16, BERT_BF16X3 = 1, 3
 
 #: every symbol include/capr_b200.h declares -> (restype, argtypes); tests check the .so exports them all
 SIGNATURES = {
@@ -37,6 +47,12 @@ SIGNATURES = {
                                    POINTER(c_void_p), POINTER(c_void_p), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_int, c_int,
                                    _f32p, _f32p, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),
+    "capr_bert_create": (c_int, [POINTER(BertConfigStruct), POINTER(c_void_p), c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "capr_bert_destroy": (None, [c_void_p]),
+    "capr_bert_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "capr_bert_forward": (c_int, [c_void_p, _i64p, _i64p, _i64p, c_int, c_int, _f32p, c_void_p, c_size_t, c_void_p]),
+    "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
 }
 
 

@@ -1,0 +1,632 @@
+// K5/K6 -- monoBERT / BERT-MaxP encoder behind the C ABI.
+//
+//   PTBERTMaxP_Class.predict_step                 capreolus/reranker/ptBERTMaxP.py:67-96
+//     self.bert(ids, attention_mask, token_type_ids)[0][:, 1]                      :82
+//   = HF transformers BertForSequenceClassification (third party; math restated in oracle/restated.py):
+//     embeddings (word + position + token_type, LayerNorm eps 1e-12)
+//     L x { QKV Linear, softmax(QK^T/sqrt(dh) + key mask) V, out Linear, +residual LayerNorm,
+//           Linear H->I, erf-GELU, Linear I->H, +residual LayerNorm }
+//     pooler tanh(Linear(x[CLS])), classifier Linear(H, 2)
+//
+// Kernels in this file: embedding+LayerNorm, fp32->(hi,lo) bf16 split, residual LayerNorm, fused masked attention
+// (fp32 FFMA flash-style, v1), pooler+classifier; the Linear layers run on tcgen05 (bert_gemm.cuh).
+#include <cuda.h>
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "bert_gemm.cuh"
+
+namespace capr {
+namespace bert {
+
+// ---------------------------------------------------------------------------------------------------------------
+// elementwise / normalisation kernels (HBM-bound, one warp per token row)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, l;
+    split_bf16(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// LayerNorm of one row held as `per` values per lane (H <= 32*MAXPER); biased variance, eps inside the sqrt (torch).
+template <int MAXPER>
+__device__ __forceinline__ void warp_layernorm_store(float (&v)[MAXPER], int H, int lane, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
+                                                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) s += (lane + 32 * i < H) ? v[i] : 0.f;
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const float d = (lane + 32 * i < H) ? v[i] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) {
+      const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      out_f32[c] = y;
+      __nv_bfloat16 h, l;
+      split_bf16(y, h, l);
+      out_hi[c] = h;
+      out_lo[c] = l;
+    }
+  }
+}
+
+constexpr int LN_MAXPER = 32;  // hidden size <= 1024
+
+// x = LayerNorm(word[id] + pos[t] + type[seg]);  T = n_seq * L tokens, position = token index inside its sequence.
+__global__ void __launch_bounds__(256) embed_ln_kernel(const long long* __restrict__ ids, const long long* __restrict__ seg, int T, int L,
+                                                       int H, int vocab, int max_pos, int type_vocab, const float* __restrict__ word,
+                                                       const float* __restrict__ pos, const float* __restrict__ type,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                       float* __restrict__ x, __nv_bfloat16* __restrict__ x_hi,
+                                                       __nv_bfloat16* __restrict__ x_lo) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= T) return;
+  long long id = ids[row], sg = seg[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  sg = sg < 0 ? 0 : (sg >= type_vocab ? type_vocab - 1 : sg);
+  const int p = row % L;
+  const float* w = word + (size_t)id * H;
+  const float* pe = pos + (size_t)(p < max_pos ? p : max_pos - 1) * H;
+  const float* te = type + (size_t)sg * H;
+  float v[LN_MAXPER];
+#pragma unroll
+  for (int i = 0; i < LN_MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < H ? (w[c] + te[c]) + pe[c] : 0.f;  // HF: inputs_embeds + token_type_embeddings, then + position_embeddings
+  }
+  warp_layernorm_store<LN_MAXPER>(v, H, lane, gamma, beta, eps, x + (size_t)row * H, x_hi + (size_t)row * H, x_lo + (size_t)row * H);
+}
+
+// x = LayerNorm(y)  (y already holds dense(out) + bias + residual from the GEMM epilogue)
+__global__ void __launch_bounds__(256) ln_kernel(const float* __restrict__ y, int T, int H, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float eps, float* __restrict__ x,
+                                                 __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const float* yr = y + (size_t)row * H;
+  float v[LN_MAXPER];
+#pragma unroll
+  for (int i = 0; i < LN_MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < H ? yr[c] : 0.f;
+  }
+  warp_layernorm_store<LN_MAXPER>(v, H, lane, gamma, beta, eps, x + (size_t)row * H, x_hi + (size_t)row * H, x_lo + (size_t)row * H);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention: ctx = softmax(Q K^T / sqrt(dh) + key_mask) V, fp32, one CTA per (sequence, head, 64-query block)
+// ---------------------------------------------------------------------------------------------------------------
+// qkv [T, 3H] fp32 (Q | K | V, each head-major inside H); mask [n_seq, L] (1 = attend); output split into bf16 planes
+// [T, H] for the out-projection GEMM.  Online softmax over key tiles of 64; tiles past the last unmasked key are
+// skipped (masked keys get weight exactly 0, as torch's finfo.min additive mask does after softmax).
+constexpr int ATT_BQ = 64, ATT_BK = 64, ATT_THREADS = 256;
+
+template <int DH>
+constexpr size_t attention_smem_bytes() { return (size_t)(3 * DH * 64 + 64 * 64 + 64) * sizeof(float) + 16; }
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __restrict__ qkv, const long long* __restrict__ mask, int L,
+                                                                int H, int heads, float scale_log2e, __nv_bfloat16* __restrict__ ctx_hi,
+                                                                __nv_bfloat16* __restrict__ ctx_lo) {
+  constexpr int DPT = DH / 16;  // output dims per thread
+  extern __shared__ __align__(16) float att_smem[];
+  float (*Qt)[ATT_BQ] = reinterpret_cast<float (*)[ATT_BQ]>(att_smem);                    // Q^T [k][row], pre-scaled by scale*log2(e)
+  float (*Kt)[ATT_BK] = reinterpret_cast<float (*)[ATT_BK]>(att_smem + DH * ATT_BQ);      // K^T [k][key ^ swz(k)]
+  float (*Vs)[DH] = reinterpret_cast<float (*)[DH]>(att_smem + 2 * DH * 64);              // V   [key][d]
+  float (*Pt)[ATT_BQ] = reinterpret_cast<float (*)[ATT_BQ]>(att_smem + 3 * DH * 64);      // P^T [key][row ^ swz(key)]
+  float* kbias = att_smem + 3 * DH * 64 + 64 * 64;
+  int* s_kv_len = reinterpret_cast<int*>(kbias + 64);
+
+  const int qblocks = (L + ATT_BQ - 1) / ATT_BQ;
+  const int qb = blockIdx.x % qblocks, head = (blockIdx.x / qblocks) % heads, seq = blockIdx.x / (qblocks * heads);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows ty*4..+3, keys / dims tx*4..+3
+  const size_t tok0 = (size_t)seq * L;
+  const int ld = 3 * H;
+  const float* Qg = qkv + tok0 * ld + head * DH;
+  const float* Kg = Qg + H;
+  const float* Vg = Qg + 2 * H;
+  const long long* mrow = mask + (size_t)seq * L;
+
+  if (tid == 0) *s_kv_len = 0;
+  __syncthreads();
+  int last = 0;
+  for (int j = tid; j < L; j += ATT_THREADS)
+    if (mrow[j] != 0) last = j + 1;
+  if (last) atomicMax(s_kv_len, last);
+  for (int i = tid; i < ATT_BQ * DH; i += ATT_THREADS) {
+    const int r = i / DH, k = i - r * DH;
+    const int row = qb * ATT_BQ + r;
+    Qt[k][r] = row < L ? Qg[(size_t)row * ld + k] * scale_log2e : 0.f;
+  }
+  __syncthreads();
+  const int kv_len = *s_kv_len;
+
+  float m_run[4], l_run[4], o[4][DPT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DPT; ++d) o[i][d] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < kv_len; k0 += ATT_BK) {
+    // coalesced global reads (consecutive threads = consecutive dims of one key); the XOR on the key's 4-group index
+    // spreads the transposed stores over the banks while keeping 4 consecutive keys contiguous for the float4 reads
+    for (int i = tid; i < ATT_BK * DH; i += ATT_THREADS) {
+      const int c = i / DH, k = i - c * DH;
+      const int key = k0 + c;
+      const bool in = key < L;
+      Kt[k][c ^ ((k & 15) << 2)] = in ? Kg[(size_t)key * ld + k] : 0.f;
+      Vs[c][k] = in ? Vg[(size_t)key * ld + k] : 0.f;
+    }
+    if (tid < ATT_BK) {
+      const int key = k0 + tid;
+      kbias[tid] = (key < L && mrow[key] != 0) ? 0.f : -INFINITY;
+    }
+    __syncthreads();
+    // S = Q K^T (already in log2 units)
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < DH; ++k) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&Qt[k][ty * 4]);
+      const float4 k4 = *reinterpret_cast<const float4*>(&Kt[k][(tx ^ (k & 15)) << 2]);
+      const float qa[4] = {q4.x, q4.y, q4.z, q4.w}, ka[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+    }
+    // online softmax: a row is shared by the 16 threads with the same ty (one half warp)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] += kbias[tx * 4 + j];
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int o_ = 8; o_ > 0; o_ >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o_));
+      const float m_new = fmaxf(m_run[i], mx);
+      const bool dead = m_new == -INFINITY;  // every key so far is masked
+      const float corr = dead ? 1.f : ex2_approx(m_run[i] - m_new);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = dead ? 0.f : ex2_approx(s[i][j] - m_new);
+        s[i][j] = p;
+        rs += p;
+      }
+#pragma unroll
+      for (int o_ = 8; o_ > 0; o_ >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o_);
+      l_run[i] = l_run[i] * corr + rs;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int d = 0; d < DPT; ++d) o[i][d] *= corr;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key = tx * 4 + j;
+      *reinterpret_cast<float4*>(&Pt[key][(ty ^ tx) << 2]) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+    }
+    __syncthreads();
+    // O += P V
+#pragma unroll 8
+    for (int c = 0; c < ATT_BK; ++c) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&Pt[c][(ty ^ (c >> 2)) << 2]);
+      const float pa[4] = {p4.x, p4.y, p4.z, p4.w};
+      float va[DPT];
+#pragma unroll
+      for (int d = 0; d < DPT; ++d) va[d] = Vs[c][tx * DPT + d];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int d = 0; d < DPT; ++d) o[i][d] = fmaf(pa[i], va[d], o[i][d]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = qb * ATT_BQ + ty * 4 + i;
+    if (row >= L) continue;
+    const float inv = l_run[i] > 0.f ? 1.0f / l_run[i] : 0.f;
+    const size_t off = (tok0 + row) * H + head * DH + tx * DPT;
+#pragma unroll
+    for (int d = 0; d < DPT; ++d) {
+      __nv_bfloat16 h, l;
+      split_bf16(o[i][d] * inv, h, l);
+      ctx_hi[off + d] = h;
+      ctx_lo[off + d] = l;
+    }
+  }
+}
+
+template <int DH>
+static int launch_attention(int grid, const float* qkv, const long long* mask, int L, int H, int heads, float scale_log2e,
+                            __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, cudaStream_t st) {
+  CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes<DH>()));
+  attention_kernel<DH><<<grid, ATT_THREADS, attention_smem_bytes<DH>(), st>>>(qkv, mask, L, H, heads, scale_log2e, ctx_hi, ctx_lo);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pooler + classifier on the [CLS] row of every sequence: logits[n, :] = Wc tanh(Wp x[n*L] + bp) + bc
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pooler_classifier_kernel(const float* __restrict__ x, int L, int H, const float* __restrict__ wp,
+                                                                const float* __restrict__ bp, const float* __restrict__ wc,
+                                                                const float* __restrict__ bc, int n_labels, float* __restrict__ logits) {
+  extern __shared__ float sm[];  // [H] cls row, [H] pooled
+  float* cls = sm;
+  float* pooled = sm + H;
+  const int seq = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + (size_t)seq * L * H;
+  for (int i = tid; i < H; i += blockDim.x) cls[i] = xr[i];
+  __syncthreads();
+  for (int j = warp; j < H; j += blockDim.x >> 5) {
+    const float* w = wp + (size_t)j * H;
+    float p = 0.f;
+    for (int k = lane; k < H; k += 32) p = fmaf(w[k], cls[k], p);
+    p = warp_sum(p);
+    if (lane == 0) pooled[j] = tanhf(p + bp[j]);
+  }
+  __syncthreads();
+  for (int c = warp; c < n_labels; c += blockDim.x >> 5) {
+    const float* w = wc + (size_t)c * H;
+    float p = 0.f;
+    for (int k = lane; k < H; k += 32) p = fmaf(w[k], pooled[k], p);
+    p = warp_sum(p);
+    if (lane == 0) logits[(size_t)seq * n_labels + c] = p + bc[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] (cols contiguous) -> TMA map with a {64, box_rows} box, 128-byte swizzle.
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  CAPR_REQUIRE(fn, CAPR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CAPR_REQUIRE(r == CUDA_SUCCESS, CAPR_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
+               (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return CAPR_OK;
+}
+
+static int pick_bn(int N) {
+  for (int bn = MAX_BN; bn >= 32; bn >>= 1)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+struct Linear {  // one nn.Linear prepared for the tensor cores
+  int N = 0, K = 0, BN = 0;
+  __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+  float* bias = nullptr;
+  CUtensorMap map_hi, map_lo;
+};
+
+struct Layer {
+  Linear qkv, attn_out, ffn1, ffn2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct Model {
+  capr_bert_config cfg;
+  int mode;  // 1 = bf16, 3 = bf16x3
+  float *word = nullptr, *pos = nullptr, *type = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<Layer> layers;
+  float *pool_w = nullptr, *pool_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  std::vector<void*> owned;
+  int sms = 0;
+};
+
+static int dev_alloc(Model* m, void** p, size_t bytes) {
+  CAPR_CHECK_CUDA(cudaMalloc(p, bytes));
+  m->owned.push_back(*p);
+  return CAPR_OK;
+}
+static int dev_copy_f32(Model* m, float** dst, const float* src, size_t n, cudaStream_t st) {
+  int rc = dev_alloc(m, (void**)dst, n * sizeof(float));
+  if (rc) return rc;
+  CAPR_CHECK_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return CAPR_OK;
+}
+
+// Build one Linear from up to three stacked [Ni, K] fp32 weights (QKV fusion) and their biases.
+static int make_linear(Model* m, Linear* lin, int K, const float* const* ws, const float* const* bs, const int* ns, int parts, cudaStream_t st) {
+  int N = 0;
+  for (int i = 0; i < parts; ++i) N += ns[i];
+  lin->N = N;
+  lin->K = K;
+  lin->BN = pick_bn(N);
+  CAPR_REQUIRE(lin->BN > 0 && K % BK == 0, CAPR_ERR_UNSUPPORTED, "capr_bert_create: Linear %dx%d needs N %% 32 == 0 and K %% 64 == 0", N, K);
+  int rc;
+  if ((rc = dev_alloc(m, (void**)&lin->w_hi, (size_t)N * K * 2))) return rc;
+  if ((rc = dev_alloc(m, (void**)&lin->w_lo, (size_t)N * K * 2))) return rc;
+  if ((rc = dev_alloc(m, (void**)&lin->bias, (size_t)N * 4))) return rc;
+  size_t row = 0;
+  for (int i = 0; i < parts; ++i) {
+    const size_t n = (size_t)ns[i] * K;
+    split_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(ws[i], n, lin->w_hi + row * K, lin->w_lo + row * K);
+    CAPR_CHECK_CUDA(cudaGetLastError());
+    CAPR_CHECK_CUDA(cudaMemcpyAsync(lin->bias + row, bs[i], (size_t)ns[i] * 4, cudaMemcpyDeviceToDevice, st));
+    row += ns[i];
+  }
+  if ((rc = make_map(&lin->map_hi, lin->w_hi, N, K, lin->BN))) return rc;
+  if ((rc = make_map(&lin->map_lo, lin->w_lo, N, K, lin->BN))) return rc;
+  return CAPR_OK;
+}
+
+template <int MODE>
+static int launch_gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const Linear& lin, int M, int epi, const float* resid,
+                       float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+  GemmArgs g{M, lin.N, lin.K, lin.BN, epi, lin.bias, resid, out_f32, out_hi, out_lo};
+  const int tiles = ((M + BM - 1) / BM) * (lin.N / lin.BN);
+  const int grid = tiles < m->sms ? tiles : m->sms;
+  CAPR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<MODE>::BYTES));
+  gemm_kernel<MODE><<<grid, GEMM_THREADS, GemmSmem<MODE>::BYTES, st>>>(a_hi, a_lo, lin.map_hi, lin.map_lo, g);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+static int gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const Linear& lin, int M, int epi, const float* resid,
+                float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+  return m->mode == 3 ? launch_gemm<3>(m, a_hi, a_lo, lin, M, epi, resid, out_f32, out_hi, out_lo, st)
+                      : launch_gemm<1>(m, a_hi, a_lo, lin, M, epi, resid, out_f32, out_hi, out_lo, st);
+}
+
+struct Workspace {
+  float *x, *y, *qkv;
+  __nv_bfloat16 *x_hi, *x_lo, *ctx_hi, *ctx_lo, *ffn_hi, *ffn_lo;
+};
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+static size_t carve(const capr_bert_config& c, size_t T, unsigned char* base, Workspace* w) {
+  const size_t Tp = (T + BM - 1) / BM * BM;
+  const size_t H = c.hidden, I = c.intermediate;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  float* x = (float*)take(Tp * H * 4);
+  float* y = (float*)take(Tp * H * 4);
+  float* qkv = (float*)take(Tp * 3 * H * 4);
+  __nv_bfloat16* x_hi = (__nv_bfloat16*)take(Tp * H * 2);
+  __nv_bfloat16* x_lo = (__nv_bfloat16*)take(Tp * H * 2);
+  __nv_bfloat16* ctx_hi = (__nv_bfloat16*)take(Tp * H * 2);
+  __nv_bfloat16* ctx_lo = (__nv_bfloat16*)take(Tp * H * 2);
+  __nv_bfloat16* ffn_hi = (__nv_bfloat16*)take(Tp * I * 2);
+  __nv_bfloat16* ffn_lo = (__nv_bfloat16*)take(Tp * I * 2);
+  if (w) *w = Workspace{x, y, qkv, x_hi, x_lo, ctx_hi, ctx_lo, ffn_hi, ffn_lo};
+  return off;
+}
+
+}  // namespace bert
+}  // namespace capr
+
+using namespace capr;
+using namespace capr::bert;
+
+extern "C" {
+
+int capr_bert_num_weights(const capr_bert_config* cfg) { return cfg ? 5 + 16 * cfg->layers + 4 : 0; }
+
+int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, int n_weights, int precision_mode, capr_stream_t stream,
+                     capr_bert_t* out) {
+  const char* fn = "capr_bert_create";
+  CAPR_REQUIRE(cfg && weights && out, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(cfg->hidden > 0 && cfg->layers > 0 && cfg->heads > 0 && cfg->intermediate > 0 && cfg->vocab > 0 && cfg->max_pos > 0 &&
+                   cfg->type_vocab > 0 && cfg->n_labels > 0,
+               CAPR_ERR_BAD_SHAPE, "%s: bad config", fn);
+  CAPR_REQUIRE(n_weights == capr_bert_num_weights(cfg), CAPR_ERR_BAD_SHAPE, "%s: expected %d weight pointers, got %d", fn,
+               capr_bert_num_weights(cfg), n_weights);
+  CAPR_REQUIRE(precision_mode == CAPR_BERT_BF16 || precision_mode == CAPR_BERT_BF16X3, CAPR_ERR_BAD_SHAPE, "%s: unknown precision mode %d", fn, precision_mode);
+  CAPR_REQUIRE(cfg->hidden % cfg->heads == 0, CAPR_ERR_BAD_SHAPE, "%s: hidden %% heads != 0", fn);
+  const int dh = cfg->hidden / cfg->heads;
+  CAPR_REQUIRE(dh == 16 || dh == 32 || dh == 64, CAPR_ERR_UNSUPPORTED, "%s: head dim %d not in {16,32,64}", fn, dh);
+  CAPR_REQUIRE(cfg->hidden <= 32 * LN_MAXPER && cfg->hidden % 64 == 0 && cfg->intermediate % 64 == 0, CAPR_ERR_UNSUPPORTED,
+               "%s: hidden must be a multiple of 64 and <= %d, intermediate a multiple of 64", fn, 32 * LN_MAXPER);
+  for (int i = 0; i < n_weights; ++i) CAPR_REQUIRE(weights[i], CAPR_ERR_BAD_POINTER, "%s: weight %d is null", fn, i);
+  cudaStream_t st = (cudaStream_t)stream;
+  Model* m = new (std::nothrow) Model();
+  CAPR_REQUIRE(m, CAPR_ERR_CUDA, "%s: out of host memory", fn);
+  m->cfg = *cfg;
+  m->mode = precision_mode == CAPR_BERT_BF16X3 ? 3 : 1;
+  m->sms = sm_count();
+  const size_t H = cfg->hidden, I = cfg->intermediate;
+  int rc = CAPR_OK;
+#define CAPR_TRY(expr)            \
+  do {                            \
+    if ((rc = (expr)) != CAPR_OK) { \
+      capr_bert_destroy((capr_bert_t)m); \
+      return rc;                  \
+    }                             \
+  } while (0)
+  if (m->sms <= 0) {
+    delete m;
+    set_error("%s: no CUDA device", fn);
+    return CAPR_ERR_NO_DEVICE;
+  }
+  const float* const* w = weights;
+  CAPR_TRY(dev_copy_f32(m, &m->word, w[0], (size_t)cfg->vocab * H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->pos, w[1], (size_t)cfg->max_pos * H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->type, w[2], (size_t)cfg->type_vocab * H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->emb_g, w[3], H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->emb_b, w[4], H, st));
+  m->layers.resize(cfg->layers);
+  for (int l = 0; l < cfg->layers; ++l) {
+    const float* const* p = w + 5 + 16 * l;
+    Layer& L = m->layers[l];
+    const float* qkv_w[3] = {p[0], p[2], p[4]};
+    const float* qkv_b[3] = {p[1], p[3], p[5]};
+    const int hs[3] = {(int)H, (int)H, (int)H};
+    CAPR_TRY(make_linear(m, &L.qkv, (int)H, qkv_w, qkv_b, hs, 3, st));
+    const int h1[1] = {(int)H}, i1[1] = {(int)I};
+    CAPR_TRY(make_linear(m, &L.attn_out, (int)H, p + 6, p + 7, h1, 1, st));
+    CAPR_TRY(dev_copy_f32(m, &L.ln1_g, p[8], H, st));
+    CAPR_TRY(dev_copy_f32(m, &L.ln1_b, p[9], H, st));
+    CAPR_TRY(make_linear(m, &L.ffn1, (int)H, p + 10, p + 11, i1, 1, st));
+    CAPR_TRY(make_linear(m, &L.ffn2, (int)I, p + 12, p + 13, h1, 1, st));
+    CAPR_TRY(dev_copy_f32(m, &L.ln2_g, p[14], H, st));
+    CAPR_TRY(dev_copy_f32(m, &L.ln2_b, p[15], H, st));
+  }
+  const float* const* t = w + 5 + 16 * cfg->layers;
+  CAPR_TRY(dev_copy_f32(m, &m->pool_w, t[0], H * H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->pool_b, t[1], H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->cls_w, t[2], (size_t)cfg->n_labels * H, st));
+  CAPR_TRY(dev_copy_f32(m, &m->cls_b, t[3], cfg->n_labels, st));
+#undef CAPR_TRY
+  *out = (capr_bert_t)m;
+  return CAPR_OK;
+}
+
+void capr_bert_destroy(capr_bert_t h) {
+  Model* m = (Model*)h;
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+}
+
+size_t capr_bert_workspace_bytes(capr_bert_t h, int n_seq, int L) {
+  Model* m = (Model*)h;
+  if (!m || n_seq <= 0 || L <= 0) return 0;
+  return carve(m->cfg, (size_t)n_seq * L, nullptr, nullptr);
+}
+
+int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, float* logits,
+                      void* workspace, size_t workspace_bytes, capr_stream_t stream) {
+  const char* fn = "capr_bert_forward";
+  Model* m = (Model*)h;
+  CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
+  CAPR_REQUIRE(n_seq >= 0 && L > 0, CAPR_ERR_BAD_SHAPE, "%s: n_seq=%d L=%d", fn, n_seq, L);
+  if (n_seq == 0) return CAPR_OK;
+  CAPR_REQUIRE(L <= m->cfg.max_pos, CAPR_ERR_BAD_SHAPE, "%s: sequence length %d exceeds max_position_embeddings %d", fn, L, m->cfg.max_pos);
+  CAPR_REQUIRE(ids && mask && seg && logits && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(((uintptr_t)workspace & 255) == 0, CAPR_ERR_BAD_POINTER, "%s: workspace must be 256-byte aligned", fn);
+  const size_t T = (size_t)n_seq * L;
+  CAPR_REQUIRE(T < (size_t)1 << 31, CAPR_ERR_BAD_SHAPE, "%s: too many tokens in one call (%zu); split the batch", fn, T);
+  Workspace ws;
+  const size_t need = carve(m->cfg, T, (unsigned char*)workspace, &ws);
+  CAPR_REQUIRE(workspace_bytes >= need, CAPR_ERR_BAD_SHAPE, "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = m->cfg.hidden, I = m->cfg.intermediate, heads = m->cfg.heads, dh = H / heads;
+  const int Ti = (int)T;
+  const size_t Tp = (T + BM - 1) / BM * BM;
+  int rc;
+  CUtensorMap x_hi, x_lo, c_hi, c_lo, f_hi, f_lo;
+  if ((rc = make_map(&x_hi, ws.x_hi, Tp, H, BM))) return rc;
+  if ((rc = make_map(&x_lo, ws.x_lo, Tp, H, BM))) return rc;
+  if ((rc = make_map(&c_hi, ws.ctx_hi, Tp, H, BM))) return rc;
+  if ((rc = make_map(&c_lo, ws.ctx_lo, Tp, H, BM))) return rc;
+  if ((rc = make_map(&f_hi, ws.ffn_hi, Tp, I, BM))) return rc;
+  if ((rc = make_map(&f_lo, ws.ffn_lo, Tp, I, BM))) return rc;
+  if (Tp > T) {  // rows past T of the A operands are read by TMA: keep them finite
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.x_hi + T * H, 0, (Tp - T) * H * 2, st));
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.x_lo + T * H, 0, (Tp - T) * H * 2, st));
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.ctx_hi + T * H, 0, (Tp - T) * H * 2, st));
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.ctx_lo + T * H, 0, (Tp - T) * H * 2, st));
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.ffn_hi + T * I, 0, (Tp - T) * I * 2, st));
+    CAPR_CHECK_CUDA(cudaMemsetAsync(ws.ffn_lo + T * I, 0, (Tp - T) * I * 2, st));
+  }
+  const int row_blocks = (Ti + 7) / 8;  // 8 warps (rows) per 256-thread CTA
+  embed_ln_kernel<<<row_blocks, 256, 0, st>>>((const long long*)ids, (const long long*)seg, Ti, L, H, m->cfg.vocab, m->cfg.max_pos,
+                                              m->cfg.type_vocab, m->word, m->pos, m->type, m->emb_g, m->emb_b, m->cfg.ln_eps, ws.x, ws.x_hi,
+                                              ws.x_lo);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
+  const int att_grid = n_seq * heads * ((L + ATT_BQ - 1) / ATT_BQ);
+  for (int l = 0; l < m->cfg.layers; ++l) {
+    const Layer& ly = m->layers[l];
+    if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;
+    if (dh == 64) rc = launch_attention<64>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+    else if (dh == 32) rc = launch_attention<32>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+    else rc = launch_attention<16>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+    if (rc) return rc;
+    if ((rc = gemm(m, c_hi, c_lo, ly.attn_out, Ti, EPI_BIAS_RESID_F32, ws.x, ws.y, nullptr, nullptr, st))) return rc;
+    ln_kernel<<<row_blocks, 256, 0, st>>>(ws.y, Ti, H, ly.ln1_g, ly.ln1_b, m->cfg.ln_eps, ws.x, ws.x_hi, ws.x_lo);
+    CAPR_CHECK_CUDA(cudaGetLastError());
+    if ((rc = gemm(m, x_hi, x_lo, ly.ffn1, Ti, EPI_BIAS_GELU_SPLIT, nullptr, nullptr, ws.ffn_hi, ws.ffn_lo, st))) return rc;
+    if ((rc = gemm(m, f_hi, f_lo, ly.ffn2, Ti, EPI_BIAS_RESID_F32, ws.x, ws.y, nullptr, nullptr, st))) return rc;
+    ln_kernel<<<row_blocks, 256, 0, st>>>(ws.y, Ti, H, ly.ln2_g, ly.ln2_b, m->cfg.ln_eps, ws.x, ws.x_hi, ws.x_lo);
+    CAPR_CHECK_CUDA(cudaGetLastError());
+  }
+  pooler_classifier_kernel<<<n_seq, 256, 2 * H * sizeof(float), st>>>(ws.x, L, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, m->cfg.n_labels, logits);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+// Debug / test entry: C = A . W^T + bias through the same tcgen05 kernel (A [M,K], W [N,K], fp32 device buffers).
+int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c, capr_stream_t stream) {
+  const char* fn = "capr_gemm_test";
+  CAPR_REQUIRE(a && w && bias && c, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0 && pick_bn(N) > 0, CAPR_ERR_BAD_SHAPE, "%s: need K %% 64 == 0 and N %% 32 == 0", fn);
+  cudaStream_t st = (cudaStream_t)stream;
+  Model m;
+  m.mode = precision_mode == CAPR_BERT_BF16X3 ? 3 : 1;
+  m.sms = sm_count();
+  CAPR_REQUIRE(m.sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  Linear lin;
+  const float* ws[1] = {w};
+  const float* bs[1] = {bias};
+  const int ns[1] = {N};
+  int rc = make_linear(&m, &lin, K, ws, bs, ns, 1, st);
+  const size_t Mp = ((size_t)M + BM - 1) / BM * BM;
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;
+  if (!rc) rc = dev_alloc(&m, (void**)&a_hi, Mp * K * 2);
+  if (!rc) rc = dev_alloc(&m, (void**)&a_lo, Mp * K * 2);
+  CUtensorMap ma_hi, ma_lo;
+  if (!rc) {
+    cudaMemsetAsync(a_hi, 0, Mp * K * 2, st);
+    cudaMemsetAsync(a_lo, 0, Mp * K * 2, st);
+    split_kernel<<<1024, 256, 0, st>>>(a, (size_t)M * K, a_hi, a_lo);
+    rc = make_map(&ma_hi, a_hi, Mp, K, BM);
+  }
+  if (!rc) rc = make_map(&ma_lo, a_lo, Mp, K, BM);
+  if (!rc) rc = gemm(&m, ma_hi, ma_lo, lin, M, EPI_BIAS_F32, nullptr, c, nullptr, nullptr, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (void* p : m.owned) cudaFree(p);
+  if (!rc && e != cudaSuccess) return cuda_fail(e, "capr_gemm_test");
+  return rc;
+}
+
+}  // extern "C"

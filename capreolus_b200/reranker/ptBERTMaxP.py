@@ -1,0 +1,197 @@
+"""monoBERT / BERT-MaxP behind the reference's module API (``capreolus/reranker/ptBERTMaxP.py``).
+
+``PTBERTMaxP_Class`` keeps the HF ``BertForSequenceClassification`` as ``self.bert`` exactly like the reference (so
+``state_dict`` keys, ``save_weights`` / ``load_weights`` and ``from_pretrained`` behave the same); in eval mode its
+``forward`` does not run the torch module but the sm_100a encoder behind ``capr_bert_forward`` (tcgen05 GEMMs), built
+lazily from the module's current parameters.  Passage aggregation (max / first / sum / avg) is the reference's
+(``ptBERTMaxP.py:85-94``), including ``avg`` dividing by the passage-mask sum of the whole batch.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from capreolus_b200 import _lib
+from capreolus_b200.module import ConfigOption, Dependency
+from capreolus_b200.reranker import Reranker
+
+_LAYER_KEYS = [
+    "attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight", "attention.self.key.bias",
+    "attention.self.value.weight", "attention.self.value.bias", "attention.output.dense.weight", "attention.output.dense.bias",
+    "attention.output.LayerNorm.weight", "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
+    "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias",
+]
+
+
+def bert_weight_keys(n_layers: int) -> list[str]:
+    """state_dict keys of a HF BertForSequenceClassification in the order ``capr_bert_create`` expects them."""
+    keys = ["bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+            "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias"]
+    for i in range(n_layers):
+        keys += [f"bert.encoder.layer.{i}.{k}" for k in _LAYER_KEYS]
+    return keys + ["bert.pooler.dense.weight", "bert.pooler.dense.bias", "classifier.weight", "classifier.bias"]
+
+
+class BertEngine:
+    """Owns one ``capr_bert_t`` handle (a snapshot of the weights as bf16 planes + TMA descriptors) and its workspace."""
+
+    PRECISION = {"bf16x3": _lib.BERT_BF16X3, "bf16": _lib.BERT_BF16}
+
+    def __init__(self, hf_model, precision="bf16x3", max_seqs_per_call=128):
+        cfg = hf_model.config
+        if cfg.model_type != "bert":
+            raise ValueError(f"capreolus_b200 ptBERTMaxP supports BERT encoders only, got {cfg.model_type!r}")
+        if getattr(cfg, "hidden_act", "gelu") != "gelu":
+            raise ValueError("capreolus_b200 ptBERTMaxP: only hidden_act='gelu' (erf) is implemented")
+        if getattr(cfg, "position_embedding_type", "absolute") != "absolute":
+            raise ValueError("capreolus_b200 ptBERTMaxP: only absolute position embeddings are implemented")
+        state = hf_model.state_dict()
+        keys = bert_weight_keys(cfg.num_hidden_layers)
+        tensors = [state[k].detach().float().contiguous() for k in keys]
+        _lib.require_cuda(*tensors)
+        self.device = tensors[0].device
+        self.n_labels = state["classifier.weight"].shape[0]
+        self.cfg = _lib.BertConfigStruct(cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size,
+                                         cfg.vocab_size, cfg.max_position_embeddings, cfg.type_vocab_size, self.n_labels,
+                                         float(cfg.layer_norm_eps))
+        ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        handle = ctypes.c_void_p()
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.capr_bert_create(ctypes.byref(self.cfg), ptrs, len(tensors), self.PRECISION[precision],
+                                            _lib.current_stream(self.device), ctypes.byref(handle)))
+            torch.cuda.current_stream(self.device).synchronize()  # the snapshot copies read `tensors`
+        self.handle = handle
+        self.max_seqs_per_call = int(max_seqs_per_call)
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().capr_bert_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def logits(self, ids, mask, seg) -> torch.Tensor:
+        """``[N,L]`` int64 x3 -> classifier logits ``[N,n_labels]`` fp32."""
+        _lib.require_cuda(ids, mask, seg)
+        lib = _lib.lib()
+        ids, mask, seg = (t.long().contiguous() for t in (ids, mask, seg))
+        N, L = ids.shape
+        out = torch.empty((N, self.n_labels), dtype=torch.float32, device=ids.device)
+        step = max(1, self.max_seqs_per_call)
+        with torch.cuda.device(ids.device):
+            for lo in range(0, N, step):
+                n = min(step, N - lo)
+                need = lib.capr_bert_workspace_bytes(self.handle, n, L)
+                if self._workspace is None or self._workspace.numel() < need or self._workspace.device != ids.device:
+                    self._workspace = torch.empty(need, dtype=torch.uint8, device=ids.device)
+                _lib.check(lib.capr_bert_forward(self.handle, ids[lo:lo + n].data_ptr(), mask[lo:lo + n].data_ptr(), seg[lo:lo + n].data_ptr(), n, L,
+                                                 out[lo:lo + n].data_ptr(), self._workspace.data_ptr(), self._workspace.numel(),
+                                                 _lib.current_stream(ids.device)))
+        return out
+
+
+class PTBERTMaxP_Class(nn.Module):
+    """``PTBERTMaxP_Class`` (capreolus/reranker/ptBERTMaxP.py:29-96)."""
+
+    def __init__(self, extractor, config, *args, **kwargs):
+        super(PTBERTMaxP_Class, self).__init__(*args, **kwargs)
+        import transformers
+
+        self.extractor = extractor
+        pretrained = config["pretrained"]
+        if isinstance(pretrained, dict):
+            # offline extension: a BertConfig dict -> random-init encoder (there is no network for checkpoints here)
+            self.bert = transformers.BertForSequenceClassification(
+                transformers.BertConfig(**{**pretrained, "hidden_dropout_prob": config["hidden_dropout_prob"]}))
+        elif "electra" in pretrained or "roberta" in pretrained:
+            raise ValueError(f"capreolus_b200 ptBERTMaxP: {pretrained!r} is not a BERT encoder (Electra / RoBERTa variants are out of scope)")
+        elif pretrained == "bert-base-msmarco":
+            self.bert = transformers.AutoModelForSequenceClassification.from_pretrained("Capreolus/bert-base-msmarco")
+        else:
+            self.bert = transformers.AutoModelForSequenceClassification.from_pretrained(
+                pretrained, hidden_dropout_prob=config["hidden_dropout_prob"])
+        self.config = config
+        self.precision = config.get("precision", "bf16x3") if hasattr(config, "get") else "bf16x3"
+        self._engine, self._engine_key = None, None
+
+    def engine(self) -> BertEngine:
+        params = list(self.bert.parameters())
+        key = (params[0].device, tuple(p._version for p in params), params[0].data_ptr())
+        if self._engine is None or key != self._engine_key:
+            self._engine = BertEngine(self.bert, self.precision)
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, doc_input, doc_mask, doc_seg):
+        if self.training:
+            raise NotImplementedError("capreolus_b200 ptBERTMaxP: only inference (model.eval()) is implemented; BERT training is out of scope")
+        return self.predict_step(doc_input, doc_mask, doc_seg)
+
+    @torch.no_grad()
+    def predict_step(self, doc_input, doc_mask, doc_seg):
+        """Scores each passage and pools over passages (ptBERTMaxP.py:67-96)."""
+        _lib.require_cuda(doc_input, doc_mask, doc_seg)
+        batch_size = doc_input.shape[0]
+        num_passages = self.extractor.config["numpassages"]
+        maxseqlen = self.extractor.config["maxseqlen"]
+
+        passage_position = (doc_mask * doc_seg).sum(dim=-1)  # (B, P)
+        passage_mask = (passage_position > 5).long()  # (B, P)
+
+        doc_input = doc_input.reshape([batch_size * num_passages, maxseqlen])
+        doc_mask = doc_mask.reshape([batch_size * num_passages, maxseqlen])
+        doc_seg = doc_seg.reshape([batch_size * num_passages, maxseqlen])
+
+        passage_scores = self.engine().logits(doc_input, doc_mask, doc_seg)[:, 1]
+        passage_scores = passage_scores.reshape([batch_size, num_passages])
+
+        if self.config["aggregation"] == "max":
+            passage_scores = passage_scores.max(dim=1)[0]  # (batch size, )
+        elif self.config["aggregation"] == "first":
+            passage_scores = passage_scores[:, 0]
+        elif self.config["aggregation"] == "sum":
+            passage_scores = torch.sum(passage_mask * passage_scores, dim=1)
+        elif self.config["aggregation"] == "avg":
+            passage_scores = torch.sum(passage_mask * passage_scores, dim=1) / torch.sum(passage_mask)
+        else:
+            raise ValueError("Unknown aggregation method: {}".format(self.config["aggregation"]))
+        return passage_scores
+
+
+@Reranker.register
+class PTBERTMaxP(Reranker):
+    """PyTorch-API BERT-MaxP (monoBERT when numpassages=1).
+
+    Deeper Text Understanding for IR with Contextual Neural Language Modeling. Zhuyun Dai and Jamie Callan. SIGIR 2019."""
+
+    module_name = "ptBERTMaxP"
+
+    dependencies = [
+        Dependency(key="extractor", module="extractor", name="bertpassage"),
+        Dependency(key="trainer", module="trainer", name="pytorch"),
+    ]
+    config_spec = [
+        ConfigOption("pretrained", "bert-base-uncased",
+                     "Pretrained model: bert-base-uncased, bert-base-msmarco, or HuggingFace supported BERT models"),
+        ConfigOption("aggregation", "max"),
+        ConfigOption("hidden_dropout_prob", 0.1, "The dropout probability of BERT-like model's hidden layers."),
+        ConfigOption("precision", "bf16x3", "tensor-core operand mode: bf16x3 (parity, 3 products) or bf16 (fast, ~2e-2 rel. error)"),
+    ]
+
+    def build_model(self):
+        self.model = PTBERTMaxP_Class(self.extractor, self.config)
+        return self.model
+
+    def score(self, d):
+        return [
+            self.model(d["pos_bert_input"], d["pos_mask"], d["pos_seg"]).view(-1),
+            self.model(d["neg_bert_input"], d["neg_mask"], d["neg_seg"]).view(-1),
+        ]
+
+    def test(self, d):
+        return self.model(d["pos_bert_input"], d["pos_mask"], d["pos_seg"]).view(-1)

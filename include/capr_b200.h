@@ -110,6 +110,43 @@ int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* id
 int capr_pair_hinge(const float* pos, const float* neg, int B, float* loss, float* grad_pos, float* grad_neg,
                     capr_stream_t stream);
 
+/* ---- monoBERT / BERT-MaxP encoder -------------------------------------------------------------------
+ * PTBERTMaxP_Class.predict_step (capreolus/reranker/ptBERTMaxP.py:67-96) calls
+ * self.bert(ids, attention_mask, token_type_ids)[0], a HF BertForSequenceClassification; this handle is that
+ * encoder on tcgen05 tensor cores.  capr_bert_create SNAPSHOTS the weights (it converts the Linear weights to
+ * bf16 (hi, lo) planes); call it again after the torch parameters change.
+ *
+ * weights: HOST array of capr_bert_num_weights(cfg) = 5 + 16*layers + 4 DEVICE fp32 pointers, in this order
+ * (HF state_dict names):
+ *   bert.embeddings.word_embeddings.weight [vocab,H], position_embeddings.weight [max_pos,H],
+ *   token_type_embeddings.weight [type_vocab,H], embeddings.LayerNorm.weight [H], .bias [H];
+ *   per layer i: attention.self.query.weight [H,H], .bias, key.weight, .bias, value.weight, .bias,
+ *     attention.output.dense.weight [H,H], .bias, attention.output.LayerNorm.weight, .bias,
+ *     intermediate.dense.weight [I,H], .bias, output.dense.weight [H,I], .bias, output.LayerNorm.weight, .bias;
+ *   bert.pooler.dense.weight [H,H], .bias, classifier.weight [n_labels,H], classifier.bias.
+ * precision_mode: CAPR_BERT_BF16X3 = every fp32 operand as two bf16 planes, 3 tensor-core products per K step
+ * (meets the 1e-3 parity bar); CAPR_BERT_BF16 = plain bf16 operands (3x fewer MMAs, ~2e-2 relative error). */
+typedef struct {
+  int hidden, layers, heads, intermediate, vocab, max_pos, type_vocab, n_labels;
+  float ln_eps;
+} capr_bert_config;
+typedef struct capr_bert_opaque* capr_bert_t;
+#define CAPR_BERT_BF16 1
+#define CAPR_BERT_BF16X3 3
+int capr_bert_num_weights(const capr_bert_config* cfg);
+int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, int n_weights, int precision_mode,
+                     capr_stream_t stream, capr_bert_t* out);
+void capr_bert_destroy(capr_bert_t handle);
+/* Bytes of scratch capr_bert_forward needs for n_seq sequences of length L (256-byte aligned device buffer). */
+size_t capr_bert_workspace_bytes(capr_bert_t handle, int n_seq, int L);
+/* ids / mask / seg: [n_seq, L] int64 (mask 1 = real token; capreolus/extractor/bertpassage.py:268-284);
+ * logits [n_seq, n_labels] fp32 = the classifier output; the passage score is logits[:, 1]. */
+int capr_bert_forward(capr_bert_t handle, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L,
+                      float* logits, void* workspace, size_t workspace_bytes, capr_stream_t stream);
+/* Test hook: C[M,N] = A[M,K] . W[N,K]^T + bias through the encoder's tcgen05 GEMM kernel (synchronises the stream). */
+int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c,
+                   capr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ def table_checksum(table: np.ndarray) -> np.ndarray:
 
 
 def _state_np(model, skip=("embedding.weight",)):
-    return {f"state/{k}": v.detach().cpu().numpy() for k, v in model.state_dict().items() if not any(s in k for s in skip)}
+    return {f"state/{k}": v.detach().cpu().numpy().copy() for k, v in model.state_dict().items() if not any(s in k for s in skip)}
 
 
 def _inputs(shape_name, oov=True):

@@ -1,0 +1,89 @@
+"""GPU: the tcgen05 GEMM alone, then the BERT encoder against goldens made with the reference PTBERTMaxP_Class driving a
+seeded random-init HF BertForSequenceClassification (oracle/make_goldens.py; BASELINE.json configs[3] is 'random init')."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("mode,tol", [(3, 2e-5), (1, 2e-2)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 192, 64), (256, 256, 128), (1000, 768, 768), (640, 3072, 768), (300, 768, 3072),
+                                   (128 * 150 + 5, 2304, 768)])
+def test_tcgen05_gemm_matches_fp64_matmul(M, N, K, mode, tol):
+    from capreolus_b200 import _lib
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    want = (a.double() @ w.double().T + bias.double()).numpy()
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    c = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(_lib.lib().capr_gemm_test(ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), M, N, K, mode, c.data_ptr(), None))
+    got = c.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err < tol, err
+
+
+class Extractor:
+    def __init__(self, P, L):
+        self.embeddings = None
+        self.config = {"numpassages": P, "maxseqlen": L}
+
+
+def _build(name, aggregation="max", precision="bf16x3"):
+    from capreolus_b200 import reranker as R
+
+    g = load_golden(f"bert_{name}")
+    cfg = json.loads(str(g["config_json"]))
+    N, P, L, qlen = (int(x) for x in g["shape"])
+    torch.manual_seed(int(g["weight_seed"]))
+    keep = ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size", "vocab_size", "max_position_embeddings",
+            "type_vocab_size", "initializer_range", "layer_norm_eps", "hidden_act")
+    rr = R.PTBERTMaxP(dict(pretrained={k: cfg[k] for k in keep if k in cfg}, aggregation=aggregation, hidden_dropout_prob=0.1, precision=precision),
+                      provide={"extractor": Extractor(P, L)})
+    model = rr.build_model()
+    tot = sum(float(v.double().abs().sum()) for v in model.bert.state_dict().values() if v.dtype.is_floating_point)
+    np.testing.assert_allclose(tot, g["weight_checksum"][0], rtol=1e-9)  # same random init as the golden's
+    model.to(DEV).eval()
+    batch = {k: torch.from_numpy(g[k].astype(np.int64)).to(DEV) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+    return g, rr, model, batch
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid", "base"])
+def test_bert_logits_match_reference(name):
+    g, rr, model, b = _build(name)
+    N, P, L, _ = (int(x) for x in g["shape"])
+    flat = lambda t: t.reshape(N * P, L)
+    logits = model.engine().logits(flat(b["pos_bert_input"]), flat(b["pos_mask"]), flat(b["pos_seg"])).cpu().numpy()
+    assert rel_err(logits, g["logits"], floor=1e-2) < 1e-3
+
+
+@pytest.mark.parametrize("name,aggs", [("tiny", ["max", "first", "sum", "avg"]), ("mid", ["max", "avg"]), ("base", ["max"])])
+def test_bert_maxp_scores_match_reference(name, aggs):
+    for agg in aggs:
+        g, rr, model, b = _build(name, aggregation=agg)
+        scores = rr.test(b).cpu().numpy()
+        assert scores.shape == g[f"{agg}/scores"].shape
+        assert rel_err(scores, g[f"{agg}/scores"], floor=1e-2) < 1e-3, agg
+
+
+def test_bert_plain_bf16_mode_is_close_but_not_parity():
+    g, rr, model, b = _build("mid", precision="bf16")
+    scores = rr.test(b).cpu().numpy()
+    err = rel_err(scores, g["max/scores"], floor=1e-2)
+    assert err < 0.1, err
+
+
+def test_bert_training_mode_is_rejected():
+    g, rr, model, b = _build("tiny")
+    model.train()
+    with pytest.raises(NotImplementedError):
+        rr.test(b)
