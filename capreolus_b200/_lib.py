@@ -41,6 +41,10 @@ SIGNATURES = {
     "capr_simmat_forward": (c_int, [_i64p, _i64p, c_int, c_int, c_int, _f32p, c_int, c_int, _f32p, c_void_p]),
     "capr_knrm_forward": (c_int, [_i64p, _i64p, c_int, c_int, c_int, _f32p, c_int, c_int, _f32p, _f32p, c_int, _f32p, _f32p,
                                   c_int, _f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_table_pitch_bf16": (c_int, [c_int]),
+    "capr_table_prepare_bf16": (c_int, [_f32p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "capr_knrm_forward_tc": (c_int, [_i64p, _i64p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, _f32p, _f32p, c_int,
+                                     _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p]),
     "capr_drmm_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
                                   c_int, c_int, _f32p, _f32p, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p]),
     "capr_pacrr_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -31,6 +31,23 @@ class PreparedTable:
         self.embedding = embedding
         self._key = None
         self._table = None
+        self._key16 = None
+        self._planes = None
+
+    def get_bf16(self):
+        """(hi, lo) bf16 planes ``[V, pitch64]`` of the normalised table for the tensor-core engine (``capr_table_prepare_bf16``)."""
+        w = self.embedding.weight
+        _lib.require_cuda(w)
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self._key16:
+            V, E = w.shape
+            pitch = _lib.lib().capr_table_pitch_bf16(E)
+            src = w.detach().contiguous()
+            hi = torch.empty((V, pitch), dtype=torch.bfloat16, device=w.device)
+            lo = torch.empty((V, pitch), dtype=torch.bfloat16, device=w.device)
+            _lib.check(_lib.lib().capr_table_prepare_bf16(src.data_ptr(), V, E, hi.data_ptr(), lo.data_ptr(), pitch, _lib.current_stream(w.device)))
+            self._planes, self._key16 = (hi, lo), key
+        return self._planes
 
     @property
     def pitch(self) -> int:

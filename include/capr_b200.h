@@ -75,6 +75,19 @@ int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, in
                       int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
                       float* stats, capr_stream_t stream);
 
+/* Engine 2 (tensor cores): same contract as capr_knrm_forward (inference outputs only), but the cosine tile is
+ * computed by tcgen05.mma from a table stored as two bf16 planes, hi = bf16(e) and lo = bf16(e - hi) of the same
+ * L2-normalised rows (capr_table_prepare_bf16; pitch = capr_table_pitch_bf16(E), a multiple of 64 elements), with
+ * the three products hi.hi + hi.lo + lo.hi accumulated in fp32.  Limits: D <= 512, pitch <= 320, K <= 16 (else
+ * CAPR_ERR_UNSUPPORTED -> use capr_knrm_forward). */
+int capr_table_pitch_bf16(int E);
+int capr_table_prepare_bf16(const float* emb /*[V,E]*/, int V, int E, void* table_hi /*bf16 [V,pitch]*/,
+                            void* table_lo /*bf16 [V,pitch]*/, int pitch, capr_stream_t stream);
+int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q, int D, const void* table_hi,
+                         const void* table_lo, int V, int E, int pitch, const float* mu, const float* sigma, int K,
+                         const float* w1, const float* b1, int hidden, const float* w2, const float* b2, int flags,
+                         float* scores, float* feats, capr_stream_t stream);
+
 /* ---- DRMM -----------------------------------------------------------------------------------------
  * DRMM_class.forward (capreolus/reranker/DRMM.py:101-116): _hist_map (41-81) + ffw + _term_gate (83-99).
  *   idf [B,Q] fp32; bin_ub [nbins] = torch.linspace(-1,1,nbins+1)[1:] (device, the exact fp32 values)

@@ -67,9 +67,18 @@ def test_simmat_matches_reference(shape):
     assert np.all(sim[np.ones_like(sim, bool) & (d == 0)[:, None, :]] == 0)
 
 
+@pytest.fixture(params=["tc", "ffma"])
+def engine(request, monkeypatch):
+    """Run a test once per cosine-tile engine (tcgen05 tensor cores / fp32 CUDA cores)."""
+    from capreolus_b200.reranker import KNRM as knrm_mod
+
+    monkeypatch.setattr(knrm_mod, "ENGINE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("variant", list(KNRM_CFG))
-def test_knrm_scores_match_reference(shape, variant):
+def test_knrm_scores_match_reference(shape, variant, engine):
     g = load_golden(f"knrm_{shape}")
     rr, model = _build("KNRM", g, variant, KNRM_CFG[variant])
     b = _batch(g)
@@ -184,7 +193,7 @@ def _fresh(cls, oracle_fn, cfg, B, Q, D, V, E, seed, oov=True, **okw):
 
 
 @pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 1, 50, 16)])
-def test_knrm_fresh_shapes(B, Q, D, V, E):
+def test_knrm_fresh_shapes(B, Q, D, V, E, engine):
     got, want = _fresh("KNRM", "knrm_forward", KNRM_CFG["default"], B, Q, D, V, E, seed=31)
     assert rel_err(got, want) < TOL
 
@@ -227,7 +236,7 @@ def test_errors_and_edge_cases():
         model(d.cpu(), q[:, :8].cpu(), None)
 
 
-def test_sharded_scores_are_bitwise_identical_to_single_call():
+def test_sharded_scores_are_bitwise_identical_to_single_call(engine):
     """Per-pair arithmetic does not depend on the batch it is in: shard == whole, bit for bit."""
     from capreolus_b200.sharding import shard_bounds
 
@@ -244,7 +253,7 @@ def test_sharded_scores_are_bitwise_identical_to_single_call():
             assert torch.equal(torch.cat(parts), whole)
 
 
-def test_full_size_properties():
+def test_full_size_properties(engine):
     """BASELINE.json configs[1] size (100k pairs, |q|=32, |d|=512): size-independent properties + oracle on a sample."""
     from capreolus_b200 import reranker as R, synthetic
     from oracle import restated
