@@ -70,9 +70,9 @@ def test_simmat_matches_reference(shape):
 @pytest.fixture(params=["tc", "ffma"])
 def engine(request, monkeypatch):
     """Run a test once per cosine-tile engine (tcgen05 tensor cores / fp32 CUDA cores)."""
-    from capreolus_b200.reranker import KNRM as knrm_mod
+    import importlib
 
-    monkeypatch.setattr(knrm_mod, "ENGINE", request.param)
+    monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.KNRM"), "ENGINE", request.param)
     return request.param
 
 
