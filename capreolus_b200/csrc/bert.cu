@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "bert_gemm.cuh"
+#include "tmap.cuh"
 
 namespace capr {
 namespace bert {
@@ -301,34 +302,8 @@ __global__ void __launch_bounds__(256) pooler_classifier_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// 2-D bf16 tensor [rows, cols] (cols contiguous) -> TMA map with a {64, box_rows} box, 128-byte swizzle.
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  CAPR_REQUIRE(fn, CAPR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CAPR_REQUIRE(r == CUDA_SUCCESS, CAPR_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
-               (unsigned long long)rows, (unsigned long long)cols, box_rows);
-  return CAPR_OK;
+  return tc::make_bf16_map(m, base, rows, cols, box_rows);
 }
 
 static int pick_bn(int N) {

@@ -9,6 +9,7 @@
 // pooling epilogue (MUFU ex2 bound, 180 k exponentials per pair) runs on 8 warps while the producer and MMA warps are
 // already working on the next pair.
 #include "simtc.cuh"
+#include "tmap.cuh"
 
 namespace capr {
 
@@ -23,18 +24,17 @@ struct KnrmTcArgs {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTcArgs a) {
+__global__ void __launch_bounds__(simtc::THREADS, 1)
+knrm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const KnrmTcArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
-  float* sS = s.extra;          // [QT][KT] soft-TF
-  float* sRow = sS + QT * KT;   // [QT] cosine row sums
-  float* sFeat = sRow + QT;     // [KT]
+  float* sPart = s.extra;  // [EPI_WARPS][KT] per-warp partial features
   const uint32_t tmem_base = setup(s, tid);
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    producer_loop(s, a.pr, tid - EPI_THREADS);
+    producer_loop(s, a.pr, &tm_hi, &tm_lo, lane);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     if (lane == 0) mma_loop(s, a.pr, tmem_base);
   } else {
@@ -51,58 +51,60 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
     int it = 0;
     for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, ++it) {
       const int b = it & 1;
-      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid);
+      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid, (a.flags & CAPR_DEBUG_SKIP_DRAIN) != 0);
       acc_phase[b] ^= 1;
+      // lane k accumulates this warp's share of R_k = sum over its live rows of log(S_k + 1e-6)   (KNRM.py:50-53)
+      float R_part = 0.f;
+      if (!(a.flags & CAPR_DEBUG_SKIP_POOL)) {
 #pragma unroll
-      for (int r = 0; r < ROWS_PER_WARP; ++r) {
-        const float* row = s.sim + (warp * ROWS_PER_WARP + r) * SIM_PITCH;
-        float S[KT], rs = 0.f;
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
+          const float* row = s.sim + (warp * ROWS_PER_WARP + r) * SIM_PITCH;
+          float S[KT], rs = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) S[k] = 0.f;
-        for (int c = lane; c < a.pr.D; c += 32) {
-          const float v = row[c];
-          rs += v;
+          for (int k = 0; k < KT; ++k) S[k] = 0.f;
+          for (int c = lane; c < a.pr.D; c += 32) {
+            const float v = row[c];
+            rs += v;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              const float adj = v - mu[k];
+              S[k] += ex2_approx(cc[k] * adj * adj);
+            }
+          }
+          rs = warp_sum(rs);
+          float mine = 0.f;
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            const float adj = v - mu[k];
-            S[k] += ex2_approx(cc[k] * adj * adj);
+            const float t = warp_sum(S[k]);
+            mine = lane == k ? t : mine;
           }
-        }
-        rs = warp_sum(rs);
-#pragma unroll
-        for (int k = 0; k < KT; ++k) S[k] = warp_sum(S[k]);
-        if (lane == 0) {
-          const int q = warp * ROWS_PER_WARP + r;
-          sRow[q] = rs;
-#pragma unroll
-          for (int k = 0; k < KT; ++k) sS[q * KT + k] = S[k];
+          if (rs != 0.0f && warp * ROWS_PER_WARP + r < a.pr.Q) R_part += logf(mine + 1e-6f);  // KNRM.py:51-52
         }
       }
+      if (lane < KT) sPart[warp * KT + lane] = R_part;
       epi_barrier();
-      if (tid < a.K) {
+      if (warp == 0) {
         float R = 0.f;
-        for (int q = 0; q < a.pr.Q; ++q)
-          if (sRow[q] != 0.0f) R += logf(sS[q * KT + tid] + 1e-6f);  // KNRM.py:51-52
-        sFeat[tid] = R;
-        if (a.feats) a.feats[(size_t)pair * a.K + tid] = R;
-      }
-      epi_barrier();
-      if (a.scores && warp == 0) {
-        float out;
-        if (a.hidden == 0) {
-          float p = lane < a.K ? a.w1[lane] * sFeat[lane] : 0.f;
-          out = warp_sum(p) + a.b1[0];
-        } else {
-          float p = 0.f;
-          for (int h = lane; h < a.hidden; h += 32) {
-            float acc = a.b1[h];
-            for (int k = 0; k < a.K; ++k) acc = fmaf(a.w1[h * a.K + k], sFeat[k], acc);
-            p = fmaf(a.w2[h], tanhf(acc), p);
-          }
-          out = warp_sum(p) + a.b2[0];
+        if (lane < a.K) {
+#pragma unroll
+          for (int w = 0; w < EPI_WARPS; ++w) R += sPart[w * KT + lane];  // fixed order over the 8 row groups
+          if (a.feats) a.feats[(size_t)pair * a.K + lane] = R;
         }
-        if (a.flags & CAPR_KNRM_SCORETANH) out = tanhf(out);
-        if (lane == 0) a.scores[pair] = out;
+        if (a.scores) {
+          float out;
+          if (a.hidden == 0) {
+            out = warp_sum(lane < a.K ? a.w1[lane] * R : 0.f) + a.b1[0];
+          } else {
+            float p = 0.f;
+            for (int h = 0; h < a.hidden; ++h) {
+              const float acc = warp_sum(lane < a.K ? a.w1[h * a.K + lane] * R : 0.f) + a.b1[h];
+              p = fmaf(a.w2[h], tanhf(acc), p);
+            }
+            out = p + a.b2[0];
+          }
+          if (a.flags & CAPR_KNRM_SCORETANH) out = tanhf(out);
+          if (lane == 0) a.scores[pair] = out;
+        }
       }
       // the next drain_pair starts with an epi_barrier, which orders these reads before the next writes of s.sim / sS
     }
@@ -171,17 +173,21 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E};
   a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2, a.scores = scores, a.feats = feats;
   const int KT = K <= 11 ? 11 : 16;
-  const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, (size_t)(QT * KT + QT + KT) * sizeof(float));
+  const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, (size_t)(simtc::EPI_WARPS * KT) * sizeof(float));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;
   cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tm_hi, tm_lo;
+  int rc = tc::make_gather_map(&tm_hi, table_hi, V, pitch);
+  if (rc) return rc;
+  if ((rc = tc::make_gather_map(&tm_lo, table_lo, V, pitch))) return rc;
   if (KT == 11) {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<11><<<grid, simtc::THREADS, smem, st>>>(a);
+    knrm_tc_kernel<11><<<grid, simtc::THREADS, smem, st>>>(tm_hi, tm_lo, a);
   } else {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<16><<<grid, simtc::THREADS, smem, st>>>(a);
+    knrm_tc_kernel<16><<<grid, simtc::THREADS, smem, st>>>(tm_hi, tm_lo, a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

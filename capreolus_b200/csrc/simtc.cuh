@@ -11,13 +11,15 @@
 //     32-63), and a second MMA with N=32 adds d_lo.q_hi into columns 0-31.  cos = col[i] + col[32+i]: the three
 //     products of the (hi+lo)(hi+lo) expansion, the dropped lo.lo term is ~2^-18 relative.  CPU emulation of this
 //     arithmetic against the goldens: KNRM 8e-7, PACRR 2e-5, DRMM 0 bin flips (tests/emulate.py);
-//   * rows are gathered with 16-byte cp.async straight into the canonical SWIZZLE_128B K-major layout (8 lanes fetch
-//     one 128-byte row segment: fully coalesced), published to the tensor core with fence.proxy.async + mbarrier;
+//   * rows are gathered by the TMA unit (cp.async.bulk.tensor ... tile::gather4: four table rows per instruction)
+//     straight into the canonical SWIZZLE_128B K-major layout and completed on mbarriers -- the issuing warp never
+//     waits for data.  (A first version used 16-byte cp.async + fence.proxy.async: the fence drains every outstanding
+//     copy of the thread, which serialised the ring to one L2 round trip per stage: 7.4 M pairs/s ceiling.)
 //   * accumulators live in TMEM (4 M-tiles x 64 columns per pair, double buffered = 512 columns), so the epilogue
 //     of pair p (TMEM -> cosine tile in smem -> model-specific pooling) overlaps the gather + MMAs of pair p+1.
 //
-// Warp roles (416 threads): warps 0-7 epilogue (warp % 4 = the TMEM lane quarter it may read), warps 8-11 gather
-// producers, warp 12 = MMA issuer + TMEM allocator.
+// Warp roles (320 threads): warps 0-7 epilogue (warp % 4 = the TMEM lane quarter it may read), warp 8 = TMA gather
+// producer, warp 9 = MMA issuer + TMEM allocator.
 #pragma once
 #include "simtile.cuh"
 #include "tc_common.cuh"
@@ -25,16 +27,15 @@
 namespace capr {
 namespace simtc {
 
-constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 1;
 constexpr int EPI_THREADS = EPI_WARPS * 32, PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + PROD_THREADS + 32;
 constexpr int ATOM_K = 64;                        // bf16 elements per 128-byte swizzle row
 constexpr int MAX_ATOMS = 5;                      // pitch <= 320
 constexpr int MT = 128;                           // docs per M tile
 constexpr int Q_ATOM_BYTES = 64 * 128;            // [q_hi;q_lo] 64 rows x 128 B
-constexpr int D_PLANE_BYTES = MT * 128;           // 16 KB
-constexpr int D_STAGE_BYTES = 2 * D_PLANE_BYTES;  // hi + lo
-constexpr int D_STAGES = 2;
+constexpr int D_STAGE_BYTES = MT * 128;           // one plane (hi or lo) of 128 doc rows x one 64-element K atom = 16 KB
+constexpr int D_STAGES = 4;                       // ring depth
 constexpr int ACC_COLS_PER_MT = 64, ACC_COLS_PER_PAIR = 256;
 
 struct Smem {
@@ -78,7 +79,6 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
-__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
 struct Problem {
   const long long* q;
@@ -95,13 +95,13 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
   const int warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&s.q_full[i], PROD_THREADS);
+      tc::mbar_init(&s.q_full[i], 1);
       tc::mbar_init(&s.q_empty[i], 1);
       tc::mbar_init(&s.acc_full[i], 1);
       tc::mbar_init(&s.acc_empty[i], EPI_WARPS);
     }
     for (int i = 0; i < D_STAGES; ++i) {
-      tc::mbar_init(&s.d_full[i], PROD_THREADS);
+      tc::mbar_init(&s.d_full[i], 1);
       tc::mbar_init(&s.d_empty[i], 1);
     }
     tc::fence_barrier_init();
@@ -123,76 +123,49 @@ __device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int 
   }
 }
 
-// ---- producer warps: gather the query block and the doc stages of every pair of this CTA ----------------------------
-__device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, int ptid /*0..127*/) {
+// ---- producer warp: gather the query block and the doc stages of every pair of this CTA -----------------------------
+// One warp.  Work items, in order, per pair: the Q block, then for every (M tile, K atom): hi plane, lo plane.  An item
+// of 128 doc rows is 32 cp.async.bulk.tensor tile::gather4 instructions -- one per lane, 4 table rows each -- that the
+// TMA unit writes straight into the SWIZZLE_128B operand layout and completes on the stage's mbarrier (async proxy:
+// no fences, no waiting in the issuing thread).  All D_STAGES stages can be in flight at once.
+__device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, int lane) {
   const int atoms = pr.pitch / ATOM_K;
   const int n_mt = (pr.D + MT - 1) / MT;
-  const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
-  const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
-  uint64_t* pending = nullptr;  // full-barrier of the most recently issued item (arrive once its copies have landed)
   uint32_t q_phase[2] = {0, 0}, d_phase = 0;
   int d_stage = 0, it = 0;
-  auto publish_previous = [&](uint64_t* next) {
-    cp_async_commit();
-    if (pending) {
-      cp_async_wait<1>();
-      tc::fence_proxy_async();
-      tc::mbar_arrive(pending);
-    }
-    pending = next;
-  };
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
-    // table rows of this pair
-    if (ptid < QT) s.qrow[b * QT + ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
-    for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[b * DT + i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
-    prod_barrier();
-    // query block: rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens, all atoms
+    int* qrow = s.qrow + b * QT;
+    int* drow = s.drow + b * DT;
+    qrow[lane] = table_row(lane < pr.Q ? pr.q[(size_t)pair * pr.Q + lane] : 0, pr.V);
+    for (int i = lane; i < DT; i += 32) drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
+    __syncwarp();
+    // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     tc::mbar_wait(&s.q_empty[b], q_phase[b] ^ 1);
     q_phase[b] ^= 1;
-    {
-      const uint32_t qbase = tc::smem_u32(s.q[b]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = rsub + 16 * j;  // 0..63
-        const int tok = r & 31;
-        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[b * QT + tok] * pr.pitch + sub * 8;
-        const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
-        for (int a = 0; a < atoms; ++a)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
-      }
+    if (lane == 0) tc::mbar_expect_tx(&s.q_full[b], (uint32_t)(atoms * Q_ATOM_BYTES));
+    __syncwarp();
+    if (lane < 16) {
+      const int plane = lane >> 3, g = lane & 7;
+      const CUtensorMap* tm = plane ? tm_lo : tm_hi;
+      const int r0 = qrow[4 * g], r1 = qrow[4 * g + 1], r2 = qrow[4 * g + 2], r3 = qrow[4 * g + 3];
+      for (int a = 0; a < atoms; ++a)
+        tc::tma_gather4(s.q[b] + a * Q_ATOM_BYTES + (plane * 32 + 4 * g) * 128, tm, &s.q_full[b], a * ATOM_K, r0, r1, r2, r3);
     }
-    publish_previous(&s.q_full[b]);
     for (int mt = 0; mt < n_mt; ++mt) {
-      const __nv_bfloat16* src_hi[8];
-      const __nv_bfloat16* src_lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const size_t off = (size_t)s.drow[b * DT + mt * MT + rsub + 16 * j] * pr.pitch + sub * 8;
-        src_hi[j] = pr.hi + off;
-        src_lo[j] = pr.lo + off;
-      }
+      const int* rows = drow + mt * MT + 4 * lane;
+      const int r0 = rows[0], r1 = rows[1], r2 = rows[2], r3 = rows[3];
       for (int a = 0; a < atoms; ++a) {
-        tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
-        const uint32_t base = tc::smem_u32(s.d[d_stage]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rsub + 16 * j;
-          const uint32_t dst = base + r * 128 + ((sub ^ (r & 7)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_hi[j] + a * ATOM_K) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + D_PLANE_BYTES), "l"(src_lo[j] + a * ATOM_K) : "memory");
+        for (int plane = 0; plane < 2; ++plane) {
+          tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
+          if (lane == 0) tc::mbar_expect_tx(&s.d_full[d_stage], (uint32_t)D_STAGE_BYTES);
+          __syncwarp();
+          tc::tma_gather4(s.d[d_stage] + 4 * lane * 128, plane ? tm_lo : tm_hi, &s.d_full[d_stage], a * ATOM_K, r0, r1, r2, r3);
+          if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
         }
-        publish_previous(&s.d_full[d_stage]);
-        if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
       }
     }
-    prod_barrier();  // qrow/drow[b] are rewritten two pairs later; keep the producer threads in step
-  }
-  if (pending) {
-    cp_async_commit();
-    cp_async_wait<0>();
-    tc::fence_proxy_async();
-    tc::mbar_arrive(pending);
   }
 }
 
@@ -215,20 +188,21 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
     for (int mt = 0; mt < n_mt; ++mt) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT);
       for (int a = 0; a < atoms; ++a) {
-        tc::mbar_wait(&s.d_full[d_stage], d_phase);
-        tc::tc_fence_after();
-        const uint32_t daddr = tc::smem_u32(s.d[d_stage]);
-        const uint64_t a_hi = tc::make_sw128_kmajor_desc(daddr);
-        const uint64_t a_lo = tc::make_sw128_kmajor_desc(daddr + D_PLANE_BYTES);
         const uint64_t bq = tc::make_sw128_kmajor_desc(qaddr + a * Q_ATOM_BYTES);
         const int ksteps = min(ATOM_K, pr.E - a * ATOM_K + 15) / 16;  // skip the all-zero tail of the last atom
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
-          tc::umma_f16(d_tmem, a_hi + koff, bq + koff, idesc64, (a | k) != 0);  // [d_hi.q_hi | d_hi.q_lo]
-          tc::umma_f16(d_tmem, a_lo + koff, bq + koff, idesc32, true);           //  += d_lo.q_hi
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          tc::mbar_wait(&s.d_full[d_stage], d_phase);
+          tc::tc_fence_after();
+          const uint64_t ad = tc::make_sw128_kmajor_desc(tc::smem_u32(s.d[d_stage]));
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
+            if (plane == 0) tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc64, (a | k) != 0);  // [d_hi.q_hi | d_hi.q_lo]
+            else tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc32, true);                      //  += d_lo.q_hi
+          }
+          tc::umma_commit(&s.d_empty[d_stage]);
+          if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
         }
-        tc::umma_commit(&s.d_empty[d_stage]);
-        if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
       }
     }
     tc::umma_commit(&s.q_empty[b]);
@@ -239,7 +213,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
 // ---- epilogue helper: drain the accumulators of one pair into s.sim -------------------------------------------------
 // Called by the 256 epilogue threads.  After it returns (it ends with epi_barrier) s.sim holds the cosine tile.
 __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uint32_t tmem_base, int pair, int b, uint32_t acc_parity,
-                                           int etid) {
+                                           int etid, bool skip_stores = false) {
   const int warp = etid >> 5, lane = etid & 31, quarter = warp & 3, half = warp >> 2;
   const int n_mt = (pr.D + MT - 1) / MT;
   if (etid < QT) s.qid[etid] = id_as_int(etid < pr.Q ? pr.q[(size_t)pair * pr.Q + etid] : 0);
@@ -249,7 +223,7 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int mt = half * 2 + h;
-    if (mt < n_mt) {
+    if (mt < n_mt && !skip_stores) {
       const int doc = mt * MT + quarter * 32 + lane;
       const int did = id_as_int(doc < pr.D ? pr.d[(size_t)pair * pr.D + doc] : 0);
       const uint32_t taddr = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT) + ((uint32_t)(quarter * 32) << 16);
@@ -257,15 +231,25 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
       tc::tmem_ld_32x32(taddr, hh);
       tc::tmem_ld_32x32(taddr + 32, hl);
       tc::tmem_ld_wait();
+      // exact-match rules of simtile.cuh::store_sim_tile, branch-free: a doc token matches at most the few query
+      // positions that hold the same id, so test the cheap "any match" first (warp-uniform skip in the common case)
+      bool any = false;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float v = hh[i] + hl[i];
-        const int qi = s.qid[i];
-        if (qi == did) {  // exact-match rules of simtile.cuh::store_sim_tile
-          if (qi < 0) v += 1.0f;
-          else if (v > 0.5f) v = 1.0f;
+      for (int i = 0; i < 32; ++i) any |= (s.qid[i] == did);
+      any = any && did != 0;
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = hh[i] + hl[i];
+          const int qi = s.qid[i];
+          const bool same = qi == did;
+          v = (same && qi < 0) ? v + 1.0f : v;
+          v = (same && qi > 0 && v > 0.5f) ? 1.0f : v;
+          s.sim[i * SIM_PITCH + doc] = v;
         }
-        s.sim[i * SIM_PITCH + doc] = v;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s.sim[i * SIM_PITCH + doc] = hh[i] + hl[i];
       }
     }
   }

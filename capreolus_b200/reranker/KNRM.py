@@ -20,6 +20,7 @@ SCORETANH = 1  # CAPR_KNRM_SCORETANH
 #: cosine-tile engine for inference: "tc" = tcgen05 tensor cores (bf16 hi/lo planes), "ffma" = fp32 CUDA cores.
 #: Shapes the tensor-core kernel does not cover (maxdoclen > 512, emb dim > 320, > 16 kernels) use "ffma" automatically.
 ENGINE = os.environ.get("CAPR_SIM_ENGINE", "tc")
+_DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only (CAPR_DEBUG_SKIP_*): results invalid
 
 
 class _KnrmFeatures(torch.autograd.Function):
@@ -100,7 +101,7 @@ class KNRM_class(nn.Module):
             _lib.check(_lib.lib().capr_knrm_forward_tc(
                 q.data_ptr(), d.data_ptr(), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], E, hi.shape[1], mu.data_ptr(), sigma.data_ptr(),
                 mu.shape[0], fc1.weight.data_ptr(), fc1.bias.data_ptr(), hidden, _lib.ptr(fc2.weight if fc2 is not None else None),
-                _lib.ptr(fc2.bias if fc2 is not None else None), SCORETANH if self.p["scoretanh"] else 0, scores.data_ptr(), None,
+                _lib.ptr(fc2.bias if fc2 is not None else None), (SCORETANH if self.p["scoretanh"] else 0) | _DEBUG_FLAGS, scores.data_ptr(), None,
                 _lib.current_stream(q.device)))
             return scores
         table = self._prepared.get()

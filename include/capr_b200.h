@@ -70,6 +70,9 @@ int capr_simmat_forward(const int64_t* query, const int64_t* doc, int B, int Q, 
  *   stats  [B,2,K]   (nullable)        backward statistics for d/dmu, d/dsigma
  */
 #define CAPR_KNRM_SCORETANH 1
+/* profiling aids for capr_knrm_forward_tc only (results are NOT valid when set): skip the pooling loop / the TMEM drain */
+#define CAPR_DEBUG_SKIP_POOL 0x100
+#define CAPR_DEBUG_SKIP_DRAIN 0x200
 int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
                       int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1,
                       int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
