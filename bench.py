@@ -109,6 +109,10 @@ def host_batch(model_key, n, seed):
         b = synthetic.bert_batch(n, seqlen=BERT_L, qlen=Q, seed=seed, numpassages=1, ragged=False)
     else:
         b = synthetic.throughput_batch(n, Q, D, V, seed=seed)
+        if os.environ.get("CAPR_BENCH_IDS") == "uniform":  # experiment: no hot rows (not the BASELINE workload)
+            rng = np.random.default_rng(seed)
+            b["query"] = rng.integers(1, V, size=b["query"].shape)
+            b["posdoc"] = rng.integers(1, V, size=b["posdoc"].shape)
     return {k: torch.from_numpy(v) for k, v in b.items()}
 
 

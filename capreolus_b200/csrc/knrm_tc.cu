@@ -9,7 +9,6 @@
 // pooling epilogue (MUFU ex2 bound, 180 k exponentials per pair) runs on 8 warps while the producer and MMA warps are
 // already working on the next pair.
 #include "simtc.cuh"
-#include "tmap.cuh"
 
 namespace capr {
 
@@ -24,8 +23,7 @@ struct KnrmTcArgs {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(simtc::THREADS, 1)
-knrm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const KnrmTcArgs a) {
+__global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTcArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -34,7 +32,7 @@ knrm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const uint32_t tmem_base = setup(s, tid);
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    producer_loop(s, a.pr, &tm_hi, &tm_lo, lane);
+    producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     if (lane == 0) mma_loop(s, a.pr, tmem_base);
   } else {
@@ -178,16 +176,12 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tm_hi, tm_lo;
-  int rc = tc::make_gather_map(&tm_hi, table_hi, V, pitch);
-  if (rc) return rc;
-  if ((rc = tc::make_gather_map(&tm_lo, table_lo, V, pitch))) return rc;
   if (KT == 11) {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<11><<<grid, simtc::THREADS, smem, st>>>(tm_hi, tm_lo, a);
+    knrm_tc_kernel<11><<<grid, simtc::THREADS, smem, st>>>(a);
   } else {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<16><<<grid, simtc::THREADS, smem, st>>>(tm_hi, tm_lo, a);
+    knrm_tc_kernel<16><<<grid, simtc::THREADS, smem, st>>>(a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

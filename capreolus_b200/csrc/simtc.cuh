@@ -11,15 +11,14 @@
 //     32-63), and a second MMA with N=32 adds d_lo.q_hi into columns 0-31.  cos = col[i] + col[32+i]: the three
 //     products of the (hi+lo)(hi+lo) expansion, the dropped lo.lo term is ~2^-18 relative.  CPU emulation of this
 //     arithmetic against the goldens: KNRM 8e-7, PACRR 2e-5, DRMM 0 bin flips (tests/emulate.py);
-//   * rows are gathered by the TMA unit (cp.async.bulk.tensor ... tile::gather4: four table rows per instruction)
-//     straight into the canonical SWIZZLE_128B K-major layout and completed on mbarriers -- the issuing warp never
-//     waits for data.  (A first version used 16-byte cp.async + fence.proxy.async: the fence drains every outstanding
-//     copy of the thread, which serialised the ring to one L2 round trip per stage: 7.4 M pairs/s ceiling.)
+//   * rows are gathered with 16-byte cp.async straight into the canonical SWIZZLE_128B K-major layout (8 lanes fetch
+//     one 128-byte row segment: fully coalesced) and completed on mbarriers with cp.async.mbarrier.arrive.noinc, so
+//     the issuing threads never wait for data (see producer_loop for the two alternatives that were measured);
 //   * accumulators live in TMEM (4 M-tiles x 64 columns per pair, double buffered = 512 columns), so the epilogue
 //     of pair p (TMEM -> cosine tile in smem -> model-specific pooling) overlaps the gather + MMAs of pair p+1.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (warp % 4 = the TMEM lane quarter it may read), warp 8 = TMA gather
-// producer, warp 9 = MMA issuer + TMEM allocator.
+// Warp roles (416 threads): warps 0-7 epilogue (warp % 4 = the TMEM lane quarter it may read), warps 8-11 gather
+// producers, warp 12 = MMA issuer + TMEM allocator.
 #pragma once
 #include "simtile.cuh"
 #include "tc_common.cuh"
@@ -27,7 +26,7 @@
 namespace capr {
 namespace simtc {
 
-constexpr int EPI_WARPS = 8, PROD_WARPS = 1;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
 constexpr int EPI_THREADS = EPI_WARPS * 32, PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + PROD_THREADS + 32;
 constexpr int ATOM_K = 64;                        // bf16 elements per 128-byte swizzle row
@@ -95,13 +94,13 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
   const int warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&s.q_full[i], 1);
+      tc::mbar_init(&s.q_full[i], PROD_THREADS);
       tc::mbar_init(&s.q_empty[i], 1);
       tc::mbar_init(&s.acc_full[i], 1);
       tc::mbar_init(&s.acc_empty[i], EPI_WARPS);
     }
     for (int i = 0; i < D_STAGES; ++i) {
-      tc::mbar_init(&s.d_full[i], 1);
+      tc::mbar_init(&s.d_full[i], PROD_THREADS);
       tc::mbar_init(&s.d_empty[i], 1);
     }
     tc::fence_barrier_init();
@@ -123,50 +122,69 @@ __device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int 
   }
 }
 
-// ---- producer warp: gather the query block and the doc stages of every pair of this CTA -----------------------------
-// One warp.  Work items, in order, per pair: the Q block, then for every (M tile, K atom): hi plane, lo plane.  An item
-// of 128 doc rows is 32 cp.async.bulk.tensor tile::gather4 instructions -- one per lane, 4 table rows each -- that the
-// TMA unit writes straight into the SWIZZLE_128B operand layout and completes on the stage's mbarrier (async proxy:
-// no fences, no waiting in the issuing thread).  All D_STAGES stages can be in flight at once.
-__device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, int lane) {
+// ---- producer warps: gather the query block and the doc stages of every pair of this CTA ----------------------------
+// 4 warps.  Work items, in order, per pair: the Q block, then for every (M tile, K atom): hi plane, lo plane.  Rows are
+// copied with 16-byte cp.async straight into the SWIZZLE_128B operand layout (8 lanes fetch one 128-byte row segment:
+// fully coalesced) and each thread posts cp.async.mbarrier.arrive.noinc on the stage's barrier, which fires when ITS
+// copies have landed -- the issuing thread never waits for data, so all D_STAGES stages are in flight.  (This is the
+// cp.async -> UMMA hand-off CUTLASS uses in sm100_mma_cpasync_warpspecialized.hpp.  Two alternatives were measured and
+// dropped: wait_group + fence.proxy.async + arrive serialises on the fence, 7.4 M pairs/s ceiling; TMA tile::gather4
+// of 128-byte rows costs ~80 cycles per instruction, 2.6 M pairs/s.)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
+
+__device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, int ptid /*0..127*/) {
   const int atoms = pr.pitch / ATOM_K;
   const int n_mt = (pr.D + MT - 1) / MT;
+  const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
+  const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
   uint32_t q_phase[2] = {0, 0}, d_phase = 0;
   int d_stage = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
-    int* qrow = s.qrow + b * QT;
-    int* drow = s.drow + b * DT;
-    qrow[lane] = table_row(lane < pr.Q ? pr.q[(size_t)pair * pr.Q + lane] : 0, pr.V);
-    for (int i = lane; i < DT; i += 32) drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
-    __syncwarp();
+    if (ptid < QT) s.qrow[b * QT + ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
+    for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[b * DT + i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
+    prod_barrier();
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     tc::mbar_wait(&s.q_empty[b], q_phase[b] ^ 1);
     q_phase[b] ^= 1;
-    if (lane == 0) tc::mbar_expect_tx(&s.q_full[b], (uint32_t)(atoms * Q_ATOM_BYTES));
-    __syncwarp();
-    if (lane < 16) {
-      const int plane = lane >> 3, g = lane & 7;
-      const CUtensorMap* tm = plane ? tm_lo : tm_hi;
-      const int r0 = qrow[4 * g], r1 = qrow[4 * g + 1], r2 = qrow[4 * g + 2], r3 = qrow[4 * g + 3];
-      for (int a = 0; a < atoms; ++a)
-        tc::tma_gather4(s.q[b] + a * Q_ATOM_BYTES + (plane * 32 + 4 * g) * 128, tm, &s.q_full[b], a * ATOM_K, r0, r1, r2, r3);
+    {
+      const uint32_t qbase = tc::smem_u32(s.q[b]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rsub + 16 * j;  // 0..63
+        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[b * QT + (r & 31)] * pr.pitch + sub * 8;
+        const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
+        for (int a = 0; a < atoms; ++a)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
+      }
     }
+    cp_async_arrive_noinc(&s.q_full[b]);
     for (int mt = 0; mt < n_mt; ++mt) {
-      const int* rows = drow + mt * MT + 4 * lane;
-      const int r0 = rows[0], r1 = rows[1], r2 = rows[2], r3 = rows[3];
+      size_t off[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) off[j] = (size_t)s.drow[b * DT + mt * MT + rsub + 16 * j] * pr.pitch + sub * 8;
       for (int a = 0; a < atoms; ++a) {
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
+          const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
-          if (lane == 0) tc::mbar_expect_tx(&s.d_full[d_stage], (uint32_t)D_STAGE_BYTES);
-          __syncwarp();
-          tc::tma_gather4(s.d[d_stage] + 4 * lane * 128, plane ? tm_lo : tm_hi, &s.d_full[d_stage], a * ATOM_K, r0, r1, r2, r3);
+          const uint32_t base = tc::smem_u32(s.d[d_stage]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = rsub + 16 * j;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
+          }
+          cp_async_arrive_noinc(&s.d_full[d_stage]);
           if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
         }
       }
     }
   }
+  cp_async_commit();
+  cp_async_wait<0>();  // nothing may still be landing in shared memory when the CTA tears down
 }
 
 // ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
