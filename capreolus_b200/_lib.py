@@ -47,6 +47,11 @@ SIGNATURES = {
                                      _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p]),
     "capr_drmm_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
                                   c_int, c_int, _f32p, _f32p, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_drmm_forward_tc": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, _f32p, c_int, c_int, _f32p,
+                                     c_int, c_int, _f32p, _f32p, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_pacrr_forward_tc": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, POINTER(c_void_p), POINTER(c_void_p), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_int, c_int,
+                                      _f32p, _f32p, c_void_p]),
     "capr_pacrr_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    POINTER(c_void_p), POINTER(c_void_p), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_int, c_int,
                                    _f32p, _f32p, c_void_p]),

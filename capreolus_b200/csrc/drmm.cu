@@ -16,11 +16,12 @@
 // the reference computes when its cosines are evaluated in fp64 (tests/test_oracle.py pins this).
 // Counting is integer work: __match_any_sync groups the lanes of a warp by bin and the group leader adds
 // the group's size to a per-row shared-memory counter (no atomics, deterministic).
-#include "simtile.cuh"
+#include "simtc.cuh"
 
 namespace capr {
 
-constexpr int MAX_SLOTS = 64;  // nbins + 1
+constexpr int MAX_SLOTS = 64;     // nbins + 1 (FFMA engine)
+constexpr int MAX_SLOTS_TC = 32;  // nbins + 1 (tensor-core engine: shared memory is nearly full)
 
 struct DrmmArgs {
   const long long* q;
@@ -33,7 +34,106 @@ struct DrmmArgs {
   const float *ffw_w1, *ffw_b1, *ffw_w2, *ffw_b2, *gate_w, *out_w, *out_b;
   float* scores;
   float* hist_out;
+  simtc::Problem pr;  // tensor-core engine only
 };
+
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct EpiSync {
+  __device__ __forceinline__ void operator()() const { simtc::epi_barrier(); }
+};
+
+// Bin the `ncols` cosines of every query row of the tile (8 warps x 4 rows).  `dids` = the doc ids of these columns.
+template <int SLOTS>
+__device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid, const long long* __restrict__ dids, int ncols,
+                                                const DrmmArgs& a, const float* ub, int* cnt, int warp, int lane) {
+  const float guess_scale = 0.5f * (float)a.nbins;
+  for (int r = 0; r < 4; ++r) {
+    const int qrow = warp * 4 + r;
+    const float* row = sim + qrow * SIM_PITCH;
+    int* c_row = cnt + qrow * SLOTS;
+    const int qi = qid[qrow];
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int c = c0 + lane;
+      const long long did = c < ncols ? dids[c] : 0;
+      const bool real = did != 0;  // padded columns are pushed to +1e7: no bin (DRMM.py:59)
+      const float v = real ? row[c] : 0.f;
+      int b = (int)floorf((v + 1.0f) * guess_scale);
+      b = max(0, min(b, a.nbins));
+      while (b < a.nbins && !(v < ub[b])) ++b;
+      while (b > 0 && v < ub[b - 1]) --b;
+      // identical in-vocabulary tokens are stored as exactly 1.0f (simtile.cuh); their exact-arithmetic cosine
+      // 1 - 2e-9/|a| is < 1.0, i.e. inside the last regular bin [ub[nbins-2], 1.0) as well as the exact slot
+      if (real && v == 1.0f && qi > 0 && (long long)qi == did) b = a.nbins - 1;
+      if (!real) b = a.nbins + 1;  // sentinel group, never stored
+      const unsigned peers = __match_any_sync(0xffffffffu, b);
+      if (b < a.nbins && lane == (__ffs(peers) - 1)) c_row[b] += __popc(peers);
+      const unsigned exact = __ballot_sync(0xffffffffu, real && v > 0.999f && v < 1.001f);  // DRMM.py:66
+      if (lane == 0 && exact) c_row[a.nbins] += __popc(exact);
+      __syncwarp();
+    }
+  }
+}
+
+// counts -> +1 -> CH/NH/LCH -> 2-layer tanh feed-forward per query row -> softmax term gate -> score
+template <int SLOTS, class Sync>
+__device__ __forceinline__ void drmm_finish(const DrmmArgs& a, int pair, const int* cnt, float* z, int warp, int lane, Sync sync) {
+  const int nslots = a.nbins + 1;
+  const long long* qids = a.q + (size_t)pair * a.Q;
+  for (int r = 0; r < 4; ++r) {
+    const int qrow = warp * 4 + r;
+    if (qrow >= a.Q) continue;  // warp-uniform
+    float h0 = lane < nslots ? (float)(cnt[qrow * SLOTS + lane] + 1) : 0.f;
+    float h1 = (SLOTS > 32 && lane + 32 < nslots) ? (float)(cnt[qrow * SLOTS + (lane + 32) % SLOTS] + 1) : 0.f;
+    if (a.hist_type == CAPR_DRMM_NH) {
+      const float tot = warp_sum(h0 + h1);
+      h0 /= tot;
+      h1 /= tot;
+    } else if (a.hist_type == CAPR_DRMM_LCH) {
+      h0 = lane < nslots ? logf(h0) : 0.f;
+      h1 = lane + 32 < nslots ? logf(h1) : 0.f;
+    }
+    if (a.hist_out) {
+      float* ho = a.hist_out + ((size_t)pair * a.Q + qrow) * nslots;
+      if (lane < nslots) ho[lane] = h0;
+      if (lane + 32 < nslots) ho[lane + 32] = h1;
+    }
+    float acc2 = 0.f;
+    for (int n = 0; n < a.nodes; ++n) {
+      const float* w = a.ffw_w1 + n * nslots;
+      float p = lane < nslots ? w[lane] * h0 : 0.f;
+      if (lane + 32 < nslots) p = fmaf(w[lane + 32], h1, p);
+      p = warp_sum(p) + a.ffw_b1[n];
+      acc2 = fmaf(a.ffw_w2[n], tanhf(p), acc2);
+    }
+    if (lane == 0) z[qrow] = tanhf(acc2 + a.ffw_b2[0]);
+  }
+  sync();
+  if (warp == 0) {
+    // term gate: softmax over the Q query positions of w_g*idf (IDF) or w_g.emb[q] (TV), pads at -1e7
+    float logit = -INFINITY;
+    if (lane < a.Q) {
+      const long long qid = qids[lane];
+      const float pad_bias = (qid == 0) ? -1e7f : 0.f;  // (1 - q_mask) * -1e7   DRMM.py:89
+      float g;
+      if (a.gate_type == CAPR_DRMM_GATE_IDF) {
+        g = a.gate_w[0] * a.idf[(size_t)pair * a.Q + lane];
+      } else {
+        // DRMM.py:109 indexes the table with the raw query ids (the reference raises on OOV ids; we read <pad>)
+        const float* e = a.raw_emb + (size_t)table_row(qid, a.V) * a.E;
+        g = 0.f;
+        for (int k = 0; k < a.E; ++k) g = fmaf(a.gate_w[k], e[k], g);
+      }
+      logit = g + pad_bias;
+    }
+    const float m = warp_max(logit);
+    const float ex = lane < a.Q ? expf(logit - m) : 0.f;
+    const float den = warp_sum(ex);
+    const float x = warp_sum(lane < a.Q ? (ex / den) * z[lane] : 0.f);
+    if (lane == 0) a.scores[pair] = fmaf(a.out_w[0], x, a.out_b[0]);  // output_layer  DRMM.py:114
+  }
+}
 
 __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -43,100 +143,52 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
   float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS);             // [MAX_SLOTS]
   float* z = ub + MAX_SLOTS;                                              // [QT] ffw output per query term
   clear_sim_tile(s, tid);
-  const int nslots = a.nbins + 1;
   if (tid < a.nbins) ub[tid] = a.bin_ub[tid];
   __syncthreads();
-  const float guess_scale = 0.5f * (float)a.nbins;
-
-  constexpr int ROWS_PER_WARP = QT / (NT / 32);
   for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x) {
     for (int i = tid; i < QT * MAX_SLOTS; i += NT) cnt[i] = 0;
     const long long* qids = a.q + (size_t)pair * a.Q;
     const long long* dids = a.d + (size_t)pair * a.D;
     for (int d0 = 0; d0 < a.D; d0 += DT) {
       build_sim_tile(s, a.table, a.pitch, a.V, qids, a.Q, dids, d0, a.D, d0 == 0, tid);  // also orders the cnt reset
-      const int ncols = min(DT, a.D - d0);
-      for (int r = 0; r < ROWS_PER_WARP; ++r) {
-        const int qrow = warp * ROWS_PER_WARP + r;
-        const float* row = s.sim + qrow * SIM_PITCH;
-        int* c_row = cnt + qrow * MAX_SLOTS;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          const int c = c0 + lane;
-          const bool real = c < ncols && s.did[c] != 0;  // padded columns are pushed to +1e7: no bin (DRMM.py:59)
-          const float v = real ? row[c] : 0.f;
-          int b = (int)floorf((v + 1.0f) * guess_scale);
-          b = max(0, min(b, a.nbins));
-          while (b < a.nbins && !(v < ub[b])) ++b;
-          while (b > 0 && v < ub[b - 1]) --b;
-          // identical in-vocabulary tokens are stored as exactly 1.0f (simtile.cuh); their exact-arithmetic cosine
-          // 1 - 2e-9/|a| is < 1.0, i.e. inside the last regular bin [ub[nbins-2], 1.0) as well as the exact slot
-          const int qi = s.qid[qrow];
-          if (real && v == 1.0f && qi > 0 && qi == s.did[c]) b = a.nbins - 1;
-          if (!real) b = a.nbins + 1;  // sentinel group, never stored
-          const unsigned peers = __match_any_sync(0xffffffffu, b);
-          if (b < a.nbins && lane == (__ffs(peers) - 1)) c_row[b] += __popc(peers);
-          const unsigned exact = __ballot_sync(0xffffffffu, real && v > 0.999f && v < 1.001f);  // DRMM.py:66
-          if (lane == 0 && exact) c_row[a.nbins] += __popc(exact);
-          __syncwarp();
-        }
-      }
+      drmm_count_tile<MAX_SLOTS>(s.sim, s.qid, dids + d0, min(DT, a.D - d0), a, ub, cnt, warp, lane);
       __syncthreads();
     }
-    // per query row: +1, histogram transform, 2-layer tanh feed-forward (DRMM.py:71-78,25,106)
-    for (int r = 0; r < ROWS_PER_WARP; ++r) {
-      const int qrow = warp * ROWS_PER_WARP + r;
-      if (qrow >= a.Q) continue;  // warp-uniform
-      float h0 = lane < nslots ? (float)(cnt[qrow * MAX_SLOTS + lane] + 1) : 0.f;
-      float h1 = lane + 32 < nslots ? (float)(cnt[qrow * MAX_SLOTS + lane + 32] + 1) : 0.f;
-      if (a.hist_type == CAPR_DRMM_NH) {
-        const float tot = warp_sum(h0 + h1);
-        h0 /= tot;
-        h1 /= tot;
-      } else if (a.hist_type == CAPR_DRMM_LCH) {
-        h0 = lane < nslots ? logf(h0) : 0.f;
-        h1 = lane + 32 < nslots ? logf(h1) : 0.f;
-      }
-      if (a.hist_out) {
-        float* ho = a.hist_out + ((size_t)pair * a.Q + qrow) * nslots;
-        if (lane < nslots) ho[lane] = h0;
-        if (lane + 32 < nslots) ho[lane + 32] = h1;
-      }
-      float acc2 = 0.f;
-      for (int n = 0; n < a.nodes; ++n) {
-        const float* w = a.ffw_w1 + n * nslots;
-        float p = lane < nslots ? w[lane] * h0 : 0.f;
-        if (lane + 32 < nslots) p = fmaf(w[lane + 32], h1, p);
-        p = warp_sum(p) + a.ffw_b1[n];
-        acc2 = fmaf(a.ffw_w2[n], tanhf(p), acc2);
-      }
-      if (lane == 0) z[qrow] = tanhf(acc2 + a.ffw_b2[0]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // term gate: softmax over the Q query positions of w_g*idf (IDF) or w_g.emb[q] (TV), pads at -1e7
-      float logit = -INFINITY;
-      if (lane < a.Q) {
-        const long long qid = qids[lane];
-        const float pad_bias = (qid == 0) ? -1e7f : 0.f;  // (1 - q_mask) * -1e7   DRMM.py:89
-        float g;
-        if (a.gate_type == CAPR_DRMM_GATE_IDF) {
-          g = a.gate_w[0] * a.idf[(size_t)pair * a.Q + lane];
-        } else {
-          // DRMM.py:109 indexes the table with the raw query ids (the reference raises on OOV ids; we read <pad>)
-          const float* e = a.raw_emb + (size_t)table_row(qid, a.V) * a.E;
-          g = 0.f;
-          for (int k = 0; k < a.E; ++k) g = fmaf(a.gate_w[k], e[k], g);
-        }
-        logit = g + pad_bias;
-      }
-      const float m = warp_max(logit);
-      const float ex = lane < a.Q ? expf(logit - m) : 0.f;
-      const float den = warp_sum(ex);
-      const float x = warp_sum(lane < a.Q ? (ex / den) * z[lane] : 0.f);
-      if (lane == 0) a.scores[pair] = fmaf(a.out_w[0], x, a.out_b[0]);  // output_layer  DRMM.py:114
-    }
+    drmm_finish<MAX_SLOTS>(a, pair, cnt, z, warp, lane, BlockSync());
     __syncthreads();  // z / cnt are rewritten by the next pair
   }
+}
+
+// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh); same counting + finish code on the 8 epilogue warps.
+__global__ void __launch_bounds__(simtc::THREADS, 1) drmm_tc_kernel(const DrmmArgs a) {
+  using namespace simtc;
+  extern __shared__ unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
+  int* cnt = reinterpret_cast<int*>(s.extra);                     // [QT][MAX_SLOTS_TC]
+  float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS_TC);  // [MAX_SLOTS_TC]
+  float* z = ub + MAX_SLOTS_TC;                                   // [QT]
+  if (tid < a.nbins) ub[tid] = a.bin_ub[tid];
+  const uint32_t tmem_base = setup(s, tid);
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    producer_loop(s, a.pr, tid - EPI_THREADS);
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    if (lane == 0) mma_loop(s, a.pr, tmem_base);
+  } else {
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
+      const int b = it & 1;
+      for (int i = tid; i < QT * MAX_SLOTS_TC; i += EPI_THREADS) cnt[i] = 0;  // ordered by drain_pair's barriers
+      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid);
+      acc_phase[b] ^= 1;
+      drmm_count_tile<MAX_SLOTS_TC>(s.sim, s.qid, a.d + (size_t)pair * a.D, a.D, a, ub, cnt, warp, lane);
+      epi_barrier();
+      drmm_finish<MAX_SLOTS_TC>(a, pair, cnt, z, warp, lane, EpiSync());
+      epi_barrier();
+    }
+  }
+  teardown(s, tmem_base, tid);
 }
 
 }  // namespace capr
@@ -163,12 +215,42 @@ extern "C" int capr_drmm_forward(const int64_t* query, const int64_t* doc, const
   CAPR_REQUIRE(nbins + 1 <= MAX_SLOTS, CAPR_ERR_UNSUPPORTED, "%s: nbins=%d > %d is not supported", fn, nbins, MAX_SLOTS - 1);
   if (B == 0) return CAPR_OK;
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
-             table, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out};
+             table, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out, simtc::Problem{}};
   size_t smem = sim_tile_bytes(pitch) + (size_t)QT * MAX_SLOTS * sizeof(int) + (MAX_SLOTS + QT) * sizeof(float);
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   drmm_kernel<<<B < sms ? B : sms, NT, smem, (cudaStream_t)stream>>>(a);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+// Engine 2 (tensor cores): same contract as capr_drmm_forward; table given as bf16 (hi, lo) planes (capr_table_prepare_bf16).
+extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                                    const void* table_hi, const void* table_lo, int V, int pitch, const float* raw_emb, int E, int nbins,
+                                    const float* bin_ub, int hist_type, int gate_type, const float* ffw_w1, const float* ffw_b1,
+                                    int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w, const float* out_w,
+                                    const float* out_b, float* scores, float* hist_out, capr_stream_t stream) {
+  const char* fn = "capr_drmm_forward_tc";
+  CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && nodes > 0 && nbins > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d nodes=%d nbins=%d", fn, B, Q, D, V, E, nodes, nbins);
+  CAPR_REQUIRE(pitch >= E && pitch % 64 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 64 and >= E (capr_table_pitch_bf16)", fn, pitch);
+  CAPR_REQUIRE(hist_type >= 0 && hist_type <= 2, CAPR_ERR_BAD_SHAPE, "%s: histType should be CH, NH or LCH", fn);
+  CAPR_REQUIRE(gate_type == 0 || gate_type == 1, CAPR_ERR_BAD_SHAPE, "%s: gateType should be IDF or TV", fn);
+  CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
+  CAPR_REQUIRE(D <= DT && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K && nbins + 1 <= MAX_SLOTS_TC, CAPR_ERR_UNSUPPORTED,
+               "%s: needs maxdoclen <= %d, emb dim <= %d, nbins <= %d: use capr_drmm_forward", fn, DT, simtc::MAX_ATOMS * simtc::ATOM_K, MAX_SLOTS_TC - 1);
+  if (B == 0) return CAPR_OK;
+  CAPR_REQUIRE(query && doc && table_hi && table_lo && bin_ub && ffw_w1 && ffw_b1 && ffw_w2 && ffw_b2 && gate_w && out_w && out_b && scores, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(gate_type != CAPR_DRMM_GATE_IDF || idf, CAPR_ERR_BAD_POINTER, "%s: IDF gate needs idf", fn);
+  CAPR_REQUIRE(gate_type != CAPR_DRMM_GATE_TV || raw_emb, CAPR_ERR_BAD_POINTER, "%s: TV gate needs the raw embedding table", fn);
+  DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
+             nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
+             simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E}};
+  const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, (size_t)QT * MAX_SLOTS_TC * sizeof(int) + (MAX_SLOTS_TC + QT) * sizeof(float));
+  CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  drmm_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, (cudaStream_t)stream>>>(a);
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }

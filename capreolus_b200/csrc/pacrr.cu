@@ -10,7 +10,7 @@
 // relu(max_f x_f) == max_f relu(x_f), so ReLU is applied once after the filter max.  Each lane keeps a
 // running top-k of its columns; lanes are merged with k rounds of warp max.  The reference's [B,F,Q,D]
 // conv output (2 MB per pair and n-gram) never exists.
-#include "simtile.cuh"
+#include "simtc.cuh"
 
 namespace capr {
 
@@ -34,6 +34,14 @@ struct PacrrArgs {
   const float *l1w, *l1b, *l2w, *l2b, *l3w, *l3b;
   float* scores;
   float* topk_out;
+  simtc::Problem pr;  // tensor-core engine only
+};
+
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct EpiSync {
+  __device__ __forceinline__ void operator()() const { simtc::epi_barrier(); }
 };
 
 __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ? fmaxf(x, 0.f) : (nonlin == 2 ? tanhf(x) : x); }
@@ -41,7 +49,7 @@ __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ?
 // One n-gram module over the rows of this warp.  feat layout: [QT][qterm], this module writes columns
 // [col0, col0 + kmax).
 template <int N, int FT>
-__device__ __forceinline__ void ngram_pass(const SimTile& s, const PacrrArgs& a, int w_off, int b_off, int F, float* feat,
+__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int w_off, int b_off, int F, float* feat,
                                            int qterm, int col0, int warp, int lane) {
   constexpr int ROWS_PER_WARP = QT / (NT / 32);
   for (int r = 0; r < ROWS_PER_WARP; ++r) {
@@ -55,7 +63,7 @@ __device__ __forceinline__ void ngram_pass(const SimTile& s, const PacrrArgs& a,
 #pragma unroll
       for (int u = 0; u < N; ++u)
 #pragma unroll
-        for (int v = 0; v < N; ++v) win[u * N + v] = s.sim[(qrow + u) * SIM_PITCH + c + v];
+        for (int v = 0; v < N; ++v) win[u * N + v] = sim[(qrow + u) * SIM_PITCH + c + v];
       float best = -INFINITY;
       if (FT > 0) {
 #pragma unroll
@@ -99,7 +107,7 @@ __device__ __forceinline__ void ngram_pass(const SimTile& s, const PacrrArgs& a,
 }
 
 template <int FT>
-__device__ __forceinline__ void ngram_dispatch(int n, const SimTile& s, const PacrrArgs& a, int w_off, int b_off, float* feat,
+__device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, int w_off, int b_off, float* feat,
                                                int qterm, int col0, int warp, int lane) {
   switch (n) {
     case 1: ngram_pass<1, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
@@ -110,89 +118,123 @@ __device__ __forceinline__ void ngram_dispatch(int n, const SimTile& s, const Pa
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) pacrr_kernel(const PacrrArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  SimTile s = carve_sim_tile(smem_raw, a.pitch);
+// Everything after the cosine tile: n-gram conv/max/top-k passes, softmax(idf) channel, 3-layer combine MLP.
+// Runs on 8 warps (tid 0..255); `sync` is the barrier of exactly those warps.
+template <class Sync>
+__device__ __forceinline__ void pacrr_epilogue(const float* sim, const PacrrArgs& a, int pair, float* feat, float* h1, float* h2, int tid,
+                                               Sync sync) {
+  const int lane = tid & 31, warp = tid >> 5;
   const int ngrams = a.maxgram - a.mingram + 1;
   const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
+  for (int g = 0; g < ngrams; ++g) {
+    const int n = a.mingram + g;
+    if (a.F == 32) ngram_dispatch<32>(n, sim, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
+    else ngram_dispatch<0>(n, sim, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
+  }
+  if (a.idf && warp == 0) {
+    // softmax over the query axis of the raw idf vector, pads included (PACRR.py:47-50)
+    const float v = lane < a.Q ? a.idf[(size_t)pair * a.Q + lane] : -INFINITY;
+    const float m = warp_max(v);
+    const float e = lane < a.Q ? expf(v - m) : 0.f;
+    const float den = warp_sum(e);
+    if (lane < a.Q) feat[lane * qterm + qterm - 1] = e / den;
+  }
+  sync();
+  if (a.topk_out) {
+    const int tk = ngrams * a.kmax;
+    for (int i = tid; i < a.Q * tk; i += 256) {
+      int r = i / tk, c = i - r * tk;
+      a.topk_out[((size_t)pair * a.Q + r) * tk + c] = feat[r * qterm + c];
+    }
+  }
+  // combine: Linear(Q*qterm, C) -> act -> Linear(C, C) -> act -> Linear(C, 1)   (PACRR.py:29-40,53)
+  const int in1 = a.Q * qterm;
+  for (int o = warp; o < a.combine; o += 8) {
+    const float* w = a.l1w + (size_t)o * in1;
+    float p = 0.f;
+    for (int i = lane; i < in1; i += 32) p = fmaf(w[i], feat[i], p);  // feat is [Q][qterm] contiguous == flattened
+    p = warp_sum(p);
+    if (lane == 0) h1[o] = act(p + a.l1b[o], a.nonlin);
+  }
+  sync();
+  for (int o = warp; o < a.combine; o += 8) {
+    const float* w = a.l2w + (size_t)o * a.combine;
+    float p = 0.f;
+    for (int i = lane; i < a.combine; i += 32) p = fmaf(w[i], h1[i], p);
+    p = warp_sum(p);
+    if (lane == 0) h2[o] = act(p + a.l2b[o], a.nonlin);
+  }
+  sync();
+  if (warp == 0) {
+    float p = 0.f;
+    for (int i = lane; i < a.combine; i += 32) p = fmaf(a.l3w[i], h2[i], p);
+    p = warp_sum(p);
+    if (lane == 0) a.scores[pair] = p + a.l3b[0];
+  }
+  sync();
+}
+
+__global__ void __launch_bounds__(NT, 1) pacrr_kernel(const PacrrArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  SimTile s = carve_sim_tile(smem_raw, a.pitch);
   float* feat = reinterpret_cast<float*>(smem_raw + sim_tile_bytes(a.pitch));  // [QT][qterm]
   float* h1 = feat + QT * (MAX_GRAMS * MAX_KMAX + 1);                          // [MAX_COMBINE]
   float* h2 = h1 + MAX_COMBINE;                                                // [MAX_COMBINE]
   clear_sim_tile(s, tid);
   __syncthreads();
-
   for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x) {
     build_sim_tile(s, a.table, a.pitch, a.V, a.q + (size_t)pair * a.Q, a.Q, a.d + (size_t)pair * a.D, 0, a.D, true, tid);
-    for (int g = 0; g < ngrams; ++g) {
-      const int n = a.mingram + g;
-      if (a.F == 32) ngram_dispatch<32>(n, s, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
-      else ngram_dispatch<0>(n, s, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
-    }
-    if (a.idf && warp == 0) {
-      // softmax over the query axis of the raw idf vector, pads included (PACRR.py:47-50)
-      const float v = lane < a.Q ? a.idf[(size_t)pair * a.Q + lane] : -INFINITY;
-      const float m = warp_max(v);
-      const float e = lane < a.Q ? expf(v - m) : 0.f;
-      const float den = warp_sum(e);
-      if (lane < a.Q) feat[lane * qterm + qterm - 1] = e / den;
-    }
-    __syncthreads();
-    if (a.topk_out) {
-      const int tk = ngrams * a.kmax;
-      for (int i = tid; i < a.Q * tk; i += NT) {
-        int r = i / tk, c = i - r * tk;
-        a.topk_out[((size_t)pair * a.Q + r) * tk + c] = feat[r * qterm + c];
-      }
-    }
-    // combine: Linear(Q*qterm, C) -> act -> Linear(C, C) -> act -> Linear(C, 1)   (PACRR.py:29-40,53)
-    const int in1 = a.Q * qterm;
-    for (int o = warp; o < a.combine; o += NT / 32) {
-      const float* w = a.l1w + (size_t)o * in1;
-      float p = 0.f;
-      for (int i = lane; i < in1; i += 32) p = fmaf(w[i], feat[i], p);  // feat is [Q][qterm] contiguous == flattened
-      p = warp_sum(p);
-      if (lane == 0) h1[o] = act(p + a.l1b[o], a.nonlin);
-    }
-    __syncthreads();
-    for (int o = warp; o < a.combine; o += NT / 32) {
-      const float* w = a.l2w + (size_t)o * a.combine;
-      float p = 0.f;
-      for (int i = lane; i < a.combine; i += 32) p = fmaf(w[i], h1[i], p);
-      p = warp_sum(p);
-      if (lane == 0) h2[o] = act(p + a.l2b[o], a.nonlin);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      float p = 0.f;
-      for (int i = lane; i < a.combine; i += 32) p = fmaf(a.l3w[i], h2[i], p);
-      p = warp_sum(p);
-      if (lane == 0) a.scores[pair] = p + a.l3b[0];
-    }
-    __syncthreads();
+    pacrr_epilogue(s.sim, a, pair, feat, h1, h2, tid, BlockSync());
   }
+}
+
+// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh); the conv/top-k/MLP epilogue is unchanged.
+__global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const PacrrArgs a) {
+  using namespace simtc;
+  extern __shared__ unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
+  float* feat = s.extra;
+  float* h1 = feat + QT * (MAX_GRAMS * MAX_KMAX + 1);
+  float* h2 = h1 + MAX_COMBINE;
+  const uint32_t tmem_base = setup(s, tid);
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    producer_loop(s, a.pr, tid - EPI_THREADS);
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    if (lane == 0) mma_loop(s, a.pr, tmem_base);
+  } else {
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
+      const int b = it & 1;
+      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid);
+      acc_phase[b] ^= 1;
+      pacrr_epilogue(s.sim, a, pair, feat, h1, h2, tid, EpiSync());
+    }
+  }
+  teardown(s, tmem_base, tid);
 }
 
 }  // namespace capr
 
 using namespace capr;
 
-extern "C" int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
-                                  const float* table, int V, int pitch, int mingram, int maxgram, int nfilters, int kmax,
-                                  const float* const* conv_w, const float* const* conv_b, const float* l1w,
-                                  const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
-                                  int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream) {
-  const char* fn = "capr_pacrr_forward";
+static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                     const void* table, const void* table_lo, int V, int E, int pitch, int mingram, int maxgram, int nfilters, int kmax,
+                     const float* const* conv_w, const float* const* conv_b, const float* l1w, const float* l1b, const float* l2w,
+                     const float* l2b, const float* l3w, const float* l3b, int combine, int nonlin, float* scores, float* topk_out,
+                     capr_stream_t stream) {
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d", fn, B, Q, D, V);
   CAPR_REQUIRE(mingram >= 1 && maxgram >= mingram && nfilters > 0 && kmax > 0 && combine > 0, CAPR_ERR_BAD_SHAPE, "%s: bad config mingram=%d maxgram=%d nfilters=%d kmax=%d combine=%d", fn, mingram, maxgram, nfilters, kmax, combine);
   CAPR_REQUIRE(nonlin >= 0 && nonlin <= 2, CAPR_ERR_BAD_SHAPE, "%s: nonlinearity must be none, relu or tanh", fn);
-  CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16", fn, pitch);
-  CAPR_REQUIRE(B == 0 || (query && doc && table && conv_w && conv_b && l1w && l1b && l2w && l2b && l3w && l3b && scores), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(pitch > 0 && pitch % (tc_engine ? 64 : 16) == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of %d", fn, pitch, tc_engine ? 64 : 16);
+  CAPR_REQUIRE(B == 0 || (query && doc && table && (!tc_engine || table_lo) && conv_w && conv_b && l1w && l1b && l2w && l2b && l3w && l3b && scores), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
   CAPR_REQUIRE(D <= DT, CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d is not supported by the PACRR kernel yet", fn, D, DT);
   CAPR_REQUIRE(D >= kmax, CAPR_ERR_BAD_SHAPE, "%s: kmax=%d exceeds maxdoclen=%d", fn, kmax, D);
-  CAPR_REQUIRE(pitch <= MAX_PITCH, CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d is not supported yet", fn, MAX_PITCH);
+  CAPR_REQUIRE(pitch <= (tc_engine ? simtc::MAX_ATOMS * simtc::ATOM_K : MAX_PITCH), CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d is not supported by this engine", fn, tc_engine ? simtc::MAX_ATOMS * simtc::ATOM_K : MAX_PITCH);
   CAPR_REQUIRE(maxgram <= MAX_NGRAM && maxgram - mingram + 1 <= MAX_GRAMS, CAPR_ERR_UNSUPPORTED, "%s: maxgram=%d > %d is not supported", fn, maxgram, MAX_NGRAM);
   CAPR_REQUIRE(nfilters <= MAX_FILTERS && kmax <= MAX_KMAX && combine <= MAX_COMBINE, CAPR_ERR_UNSUPPORTED, "%s: nfilters<=%d, kmax<=%d, combine<=%d", fn, MAX_FILTERS, MAX_KMAX, MAX_COMBINE);
   if (B == 0) return CAPR_OK;
@@ -200,7 +242,8 @@ extern "C" int capr_pacrr_forward(const int64_t* query, const int64_t* doc, cons
   PacrrArgs a{};
   a.q = (const long long*)query; a.d = (const long long*)doc; a.idf = idf;
   a.B = B; a.Q = Q; a.D = D; a.V = V; a.pitch = pitch; a.mingram = mingram; a.maxgram = maxgram; a.F = nfilters;
-  a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = table;
+  a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = tc_engine ? nullptr : (const float*)table;
+  if (tc_engine) a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E};
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
   // Stage the filter taps in constant memory (stream-ordered device-to-device copies; the constant bank
   // is per device, so concurrent PACRR calls with different weights must share one stream).
@@ -213,11 +256,37 @@ extern "C" int capr_pacrr_forward(const int64_t* query, const int64_t* doc, cons
     CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * g * MAX_FILTERS, cudaMemcpyDeviceToDevice, st));
     off += nfilters * n * n;
   }
-  size_t smem = sim_tile_bytes(pitch) + (size_t)(QT * (MAX_GRAMS * MAX_KMAX + 1) + 2 * MAX_COMBINE) * sizeof(float);
-  CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t extra = (size_t)(QT * (MAX_GRAMS * MAX_KMAX + 1) + 2 * MAX_COMBINE) * sizeof(float);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
-  pacrr_kernel<<<B < sms ? B : sms, NT, smem, st>>>(a);
+  if (tc_engine) {
+    const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, extra);
+    CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pacrr_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+  } else {
+    const size_t smem = sim_tile_bytes(pitch) + extra;
+    CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pacrr_kernel<<<B < sms ? B : sms, NT, smem, st>>>(a);
+  }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
+}
+
+extern "C" int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                                  const float* table, int V, int pitch, int mingram, int maxgram, int nfilters, int kmax,
+                                  const float* const* conv_w, const float* const* conv_b, const float* l1w,
+                                  const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
+                                  int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream) {
+  return pacrr_run("capr_pacrr_forward", false, query, doc, idf, B, Q, D, table, nullptr, V, pitch, pitch, mingram, maxgram, nfilters, kmax,
+                   conv_w, conv_b, l1w, l1b, l2w, l2b, l3w, l3b, combine, nonlin, scores, topk_out, stream);
+}
+
+// Engine 2 (tensor cores): same contract; table given as bf16 (hi, lo) planes (capr_table_prepare_bf16).
+extern "C" int capr_pacrr_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                                     const void* table_hi, const void* table_lo, int V, int E, int pitch, int mingram, int maxgram,
+                                     int nfilters, int kmax, const float* const* conv_w, const float* const* conv_b, const float* l1w,
+                                     const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
+                                     int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream) {
+  return pacrr_run("capr_pacrr_forward_tc", true, query, doc, idf, B, Q, D, table_hi, table_lo, V, E, pitch, mingram, maxgram, nfilters,
+                   kmax, conv_w, conv_b, l1w, l1b, l2w, l2b, l3w, l3b, combine, nonlin, scores, topk_out, stream);
 }

@@ -41,8 +41,8 @@ struct Smem {
   unsigned char* q[2];        // [atoms][64 rows][128 B]
   unsigned char* d[D_STAGES];
   float* sim;                 // [SIM_ROWS][SIM_PITCH]
-  int* qrow;                  // [2][QT]   table rows of the pair being gathered (producer)
-  int* drow;                  // [2][DT]
+  int* qrow;                  // [QT]   table rows of the pair being gathered (producer)
+  int* drow;                  // [DT]
   int* qid;                   // [QT]      ids of the pair being drained (epilogue)
   uint64_t *q_full, *q_empty, *d_full, *d_empty, *acc_full, *acc_empty;
   uint32_t* tmem_slot;
@@ -51,7 +51,7 @@ struct Smem {
 
 __host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes) {
   return 1024 + (size_t)2 * atoms * Q_ATOM_BYTES + (size_t)D_STAGES * D_STAGE_BYTES + (size_t)SIM_ROWS * SIM_PITCH * 4 +
-         (size_t)(2 * QT + 2 * DT + QT) * 4 + 16 * 8 + 16 + extra_bytes;
+         (size_t)(QT + DT + QT) * 4 + 16 * 8 + 16 + extra_bytes;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
@@ -65,9 +65,9 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
   s.sim = reinterpret_cast<float*>(p);
   p += SIM_ROWS * SIM_PITCH * 4;
   s.qrow = reinterpret_cast<int*>(p);
-  s.drow = s.qrow + 2 * QT;
-  s.qid = s.drow + 2 * DT;
-  p += (2 * QT + 2 * DT + QT) * 4;
+  s.drow = s.qrow + QT;
+  s.qid = s.drow + DT;
+  p += (QT + DT + QT) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
   s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + D_STAGES, s.acc_full = b + 4 + 2 * D_STAGES,
   s.acc_empty = b + 6 + 2 * D_STAGES;
@@ -144,8 +144,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   int d_stage = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
-    if (ptid < QT) s.qrow[b * QT + ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
-    for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[b * DT + i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
+    prod_barrier();  // every producer thread is done reading the previous pair's rows
+    if (ptid < QT) s.qrow[ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
+    for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
     prod_barrier();
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     tc::mbar_wait(&s.q_empty[b], q_phase[b] ^ 1);
@@ -155,7 +156,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = rsub + 16 * j;  // 0..63
-        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[b * QT + (r & 31)] * pr.pitch + sub * 8;
+        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[r & 31] * pr.pitch + sub * 8;
         const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
         for (int a = 0; a < atoms; ++a)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
@@ -165,7 +166,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     for (int mt = 0; mt < n_mt; ++mt) {
       size_t off[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) off[j] = (size_t)s.drow[b * DT + mt * MT + rsub + 16 * j] * pr.pitch + sub * 8;
+      for (int j = 0; j < 8; ++j) off[j] = (size_t)s.drow[mt * MT + rsub + 16 * j] * pr.pitch + sub * 8;
       for (int a = 0; a < atoms; ++a) {
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {

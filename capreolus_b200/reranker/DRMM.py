@@ -7,6 +7,7 @@ import torch.nn as nn
 from capreolus_b200 import _lib
 from capreolus_b200.module import ConfigOption
 from capreolus_b200.reranker import Reranker
+from capreolus_b200.reranker import common
 from capreolus_b200.reranker.common import SimilarityMatrix, _ids, create_emb_layer
 
 _HIST = {"CH": 0, "NH": 1, "LCH": 2}
@@ -54,10 +55,19 @@ class DRMM_class(nn.Module):
         B, Q = q.shape
         D = d.shape[1]
         idf = query_idf.float().contiguous()
-        table = self._prepared.get()
         raw = self.embedding.weight.detach().contiguous()
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         hist = torch.empty((B, Q, self.nbins + 1), dtype=torch.float32, device=q.device) if want_hist else None
+        if common.use_tensor_cores(D, raw.shape[1]) and self.nbins <= 31:
+            hi, lo = self._prepared.get_bf16()
+            _lib.check(_lib.lib().capr_drmm_forward_tc(
+                q.data_ptr(), d.data_ptr(), idf.data_ptr(), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], hi.shape[1], raw.data_ptr(),
+                raw.shape[1], self.nbins, self._nosave_bin_ub.data_ptr(), _HIST[self.hist_type], _GATE[self.gate_type],
+                self.ffw[0].weight.data_ptr(), self.ffw[0].bias.data_ptr(), self.nodes, self.ffw[2].weight.data_ptr(),
+                self.ffw[2].bias.data_ptr(), self.gates.weight.data_ptr(), self.output_layer.weight.data_ptr(),
+                self.output_layer.bias.data_ptr(), scores.data_ptr(), _lib.ptr(hist), _lib.current_stream(q.device)))
+            return scores, hist
+        table = self._prepared.get()
         _lib.check(_lib.lib().capr_drmm_forward(
             q.data_ptr(), d.data_ptr(), idf.data_ptr(), B, Q, D, table.data_ptr(), table.shape[0], table.shape[1], raw.data_ptr(),
             raw.shape[1], self.nbins, self._nosave_bin_ub.data_ptr(), _HIST[self.hist_type], _GATE[self.gate_type],

@@ -6,21 +6,16 @@ interchange with the reference's.  ``forward`` has the same signature and return
 """
 from __future__ import annotations
 
-import os
-
 import torch
 from torch import nn
 
 from capreolus_b200 import _lib
 from capreolus_b200.module import ConfigOption
 from capreolus_b200.reranker import Reranker
+from capreolus_b200.reranker import common
 from capreolus_b200.reranker.common import PreparedTable, RbfKernelBank, SimilarityMatrix, _ids, create_emb_layer
 
 SCORETANH = 1  # CAPR_KNRM_SCORETANH
-#: cosine-tile engine for inference: "tc" = tcgen05 tensor cores (bf16 hi/lo planes), "ffma" = fp32 CUDA cores.
-#: Shapes the tensor-core kernel does not cover (maxdoclen > 512, emb dim > 320, > 16 kernels) use "ffma" automatically.
-ENGINE = os.environ.get("CAPR_SIM_ENGINE", "tc")
-_DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only (CAPR_DEBUG_SKIP_*): results invalid
 
 
 class _KnrmFeatures(torch.autograd.Function):
@@ -96,12 +91,12 @@ class KNRM_class(nn.Module):
         fc2 = None if self.p["singlefc"] else self.combine[2]
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         E = self.embedding.weight.shape[1]
-        if ENGINE == "tc" and D <= 512 and E <= 320 and mu.shape[0] <= 16:
+        if common.use_tensor_cores(D, E) and mu.shape[0] <= 16:
             hi, lo = self._prepared.get_bf16()
             _lib.check(_lib.lib().capr_knrm_forward_tc(
                 q.data_ptr(), d.data_ptr(), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], E, hi.shape[1], mu.data_ptr(), sigma.data_ptr(),
                 mu.shape[0], fc1.weight.data_ptr(), fc1.bias.data_ptr(), hidden, _lib.ptr(fc2.weight if fc2 is not None else None),
-                _lib.ptr(fc2.bias if fc2 is not None else None), (SCORETANH if self.p["scoretanh"] else 0) | _DEBUG_FLAGS, scores.data_ptr(), None,
+                _lib.ptr(fc2.bias if fc2 is not None else None), (SCORETANH if self.p["scoretanh"] else 0) | common.DEBUG_FLAGS, scores.data_ptr(), None,
                 _lib.current_stream(q.device)))
             return scores
         table = self._prepared.get()

@@ -7,6 +7,7 @@ from torch import nn
 from capreolus_b200 import _lib
 from capreolus_b200.module import ConfigOption
 from capreolus_b200.reranker import Reranker
+from capreolus_b200.reranker import common
 from capreolus_b200.reranker.common import SimilarityMatrix, _ids, create_emb_layer, device_pointer_array
 
 _NONLIN = {"none": 0, "relu": 1, "tanh": 2}
@@ -61,11 +62,20 @@ class PACRR_class(nn.Module):
         if Q != self.extractor.config["maxqlen"]:
             raise ValueError(f"query length {Q} != extractor maxqlen {self.extractor.config['maxqlen']} (PACRR.py:30,50)")
         idf = query_idf.float().contiguous() if p["idf"] else None
-        table = self._prepared.get()
         ws = [ng.conv.weight.detach().contiguous() for ng in self.ngrams]
         bs = [ng.conv.bias.detach().contiguous() for ng in self.ngrams]
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         topk = torch.empty((B, Q, len(self.ngrams) * p["kmax"]), dtype=torch.float32, device=q.device) if want_topk else None
+        if common.use_tensor_cores(D, self.embedding_dim):
+            hi, lo = self._prepared.get_bf16()
+            _lib.check(_lib.lib().capr_pacrr_forward_tc(
+                q.data_ptr(), d.data_ptr(), _lib.ptr(idf), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], self.embedding_dim, hi.shape[1],
+                p["mingram"], p["maxgram"], p["nfilters"], p["kmax"], device_pointer_array(ws), device_pointer_array(bs),
+                self.linear1.weight.data_ptr(), self.linear1.bias.data_ptr(), self.linear2.weight.data_ptr(), self.linear2.bias.data_ptr(),
+                self.linear3.weight.data_ptr(), self.linear3.bias.data_ptr(), p["combine"], _NONLIN[p["nonlinearity"]], scores.data_ptr(),
+                _lib.ptr(topk), _lib.current_stream(q.device)))
+            return scores, topk
+        table = self._prepared.get()
         _lib.check(_lib.lib().capr_pacrr_forward(
             q.data_ptr(), d.data_ptr(), _lib.ptr(idf), B, Q, D, table.data_ptr(), table.shape[0], table.shape[1], p["mingram"], p["maxgram"],
             p["nfilters"], p["kmax"], device_pointer_array(ws), device_pointer_array(bs), self.linear1.weight.data_ptr(),

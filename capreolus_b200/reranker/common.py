@@ -7,10 +7,21 @@ ABI (``capreolus_b200/_lib.py``) instead of running torch ops.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from capreolus_b200 import _lib
+
+
+#: cosine-tile engine for inference: "tc" = tcgen05 tensor cores (table as bf16 hi/lo planes), "ffma" = fp32 CUDA cores.
+#: Shapes the tensor-core kernels do not cover (maxdoclen > 512, emb dim > 320, ...) use "ffma" automatically.
+ENGINE = os.environ.get("CAPR_SIM_ENGINE", "tc")
+DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only (CAPR_DEBUG_SKIP_*): results invalid
+
+
+def use_tensor_cores(D: int, E: int) -> bool:
+    return ENGINE == "tc" and D <= 512 and E <= 320
 
 
 def create_emb_layer(weights, non_trainable=True):

@@ -108,6 +108,13 @@ int capr_drmm_forward(const int64_t* query, const int64_t* doc, const float* idf
                       int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w, const float* out_w,
                       const float* out_b, float* scores, float* hist_out, capr_stream_t stream);
 
+/* Engine 2 (tensor cores), see capr_knrm_forward_tc.  Limits: D <= 512, pitch <= 320, nbins <= 31. */
+int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                         const void* table_hi, const void* table_lo, int V, int pitch, const float* raw_emb, int E,
+                         int nbins, const float* bin_ub, int hist_type, int gate_type, const float* ffw_w1,
+                         const float* ffw_b1, int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w,
+                         const float* out_w, const float* out_b, float* scores, float* hist_out, capr_stream_t stream);
+
 /* ---- PACRR ----------------------------------------------------------------------------------------
  * PACRR_class.forward (capreolus/reranker/PACRR.py:43-54) with PACRRConvMax2dModule (57-82) fused.
  *   conv_w / conv_b: HOST arrays of (maxgram-mingram+1) device pointers, ngrams.{i}.conv.weight [F,1,n,n] / .bias [F]
@@ -119,6 +126,13 @@ int capr_pacrr_forward(const int64_t* query, const int64_t* doc, const float* id
                        const float* const* conv_w, const float* const* conv_b, const float* l1w, const float* l1b,
                        const float* l2w, const float* l2b, const float* l3w, const float* l3b, int combine,
                        int nonlin, float* scores, float* topk_out, capr_stream_t stream);
+
+/* Engine 2 (tensor cores), see capr_knrm_forward_tc.  Limits: D <= 512, pitch <= 320. */
+int capr_pacrr_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
+                          const void* table_hi, const void* table_lo, int V, int E, int pitch, int mingram, int maxgram,
+                          int nfilters, int kmax, const float* const* conv_w, const float* const* conv_b, const float* l1w,
+                          const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
+                          int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream);
 
 /* ---- pairwise losses (tests / training loop) ------------------------------------------------------
  * pair_hinge_loss (capreolus/reranker/common.py:7,101-103): loss[0] = mean(max(0, 1 - (pos - neg))),

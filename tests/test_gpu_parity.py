@@ -72,7 +72,7 @@ def engine(request, monkeypatch):
     """Run a test once per cosine-tile engine (tcgen05 tensor cores / fp32 CUDA cores)."""
     import importlib
 
-    monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.KNRM"), "ENGINE", request.param)
+    monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.common"), "ENGINE", request.param)
     return request.param
 
 
@@ -107,7 +107,7 @@ def test_knrm_features_match_reference_soft_tf(shape):
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("variant", list(DRMM_CFG))
-def test_drmm_scores_match_reference(shape, variant):
+def test_drmm_scores_match_reference(shape, variant, engine):
     """Inputs with exact matches are checked against the reference evaluated with float64 cosines (`pos64`): the fp32
     reference's own bin for identical tokens is rounding noise (tests/test_oracle.py documents it; DESIGN.md 'Exact
     matches').  Inputs without shared terms are checked against the plain fp32 reference."""
@@ -127,7 +127,7 @@ def test_drmm_scores_match_reference(shape, variant):
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_drmm_histogram_matches_reference(shape):
+def test_drmm_histogram_matches_reference(shape, engine):
     g = load_golden(f"drmm_{shape}")
     rr, model = _build("DRMM", g, "default", DRMM_CFG["default"])
     b = _batch(g)
@@ -147,7 +147,7 @@ def test_drmm_histogram_matches_reference(shape):
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("variant", list(PACRR_CFG))
-def test_pacrr_scores_match_reference(shape, variant):
+def test_pacrr_scores_match_reference(shape, variant, engine):
     g = load_golden(f"pacrr_{shape}")
     rr, model = _build("PACRR", g, variant, PACRR_CFG[variant])
     b = _batch(g)
@@ -158,7 +158,7 @@ def test_pacrr_scores_match_reference(shape, variant):
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_pacrr_topk_matches_reference(shape):
+def test_pacrr_topk_matches_reference(shape, engine):
     g = load_golden(f"pacrr_{shape}")
     rr, model = _build("PACRR", g, "default", PACRR_CFG["default"])
     b = _batch(g)
@@ -199,13 +199,13 @@ def test_knrm_fresh_shapes(B, Q, D, V, E, engine):
 
 
 @pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300)])
-def test_drmm_fresh_shapes(B, Q, D, V, E):
+def test_drmm_fresh_shapes(B, Q, D, V, E, engine):
     got, want = _fresh("DRMM", "drmm_forward", DRMM_CFG["default"], B, Q, D, V, E, seed=41, oov=False, exact_cosines=True)
     assert rel_err(got, want) < TOL
 
 
 @pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300)])
-def test_pacrr_fresh_shapes(B, Q, D, V, E):
+def test_pacrr_fresh_shapes(B, Q, D, V, E, engine):
     got, want = _fresh("PACRR", "pacrr_forward", PACRR_CFG["default"], B, Q, D, V, E, seed=51)
     assert rel_err(got, want) < TOL
 
