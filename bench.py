@@ -38,7 +38,7 @@ BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
 MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP"}
 DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024}
 DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256}
-TOP_KERNEL = {"knrm": "knrm_kernel", "drmm": "drmm_kernel", "pacrr": "pacrr_kernel", "bert": "gemm_kernel<3> (+ attention_kernel)"}
+TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_kernel)"}
 
 
 class Extractor:

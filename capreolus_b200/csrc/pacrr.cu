@@ -20,9 +20,13 @@ constexpr int MAX_KMAX = 8;
 constexpr int MAX_GRAMS = 5;     // number of n-gram modules
 constexpr int MAX_COMBINE = 128;
 constexpr int CONV_FLOATS = MAX_FILTERS * (1 + 4 + 9 + 16 + 25);
+// Window size n owns a FIXED slot of constant memory, so that with N and the filter index unrolled every tap is an
+// immediate constant-bank operand of its FFMA (no LDC, no address arithmetic in the inner loop).
+__host__ __device__ constexpr int conv_w_slot(int n) { return MAX_FILTERS * ((n - 1) * n * (2 * n - 1) / 6); }  // sum_{m<n} m^2
+__host__ __device__ constexpr int conv_b_slot(int n) { return MAX_FILTERS * (n - 1); }
 
 __constant__ float c_conv_w[CONV_FLOATS];
-__constant__ float c_conv_b[MAX_GRAMS * MAX_FILTERS];
+__constant__ float c_conv_b[MAX_NGRAM * MAX_FILTERS];
 
 struct PacrrArgs {
   const long long* q;
@@ -49,8 +53,8 @@ __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ?
 // One n-gram module over the rows of this warp.  feat layout: [QT][qterm], this module writes columns
 // [col0, col0 + kmax).
 template <int N, int FT>
-__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int w_off, int b_off, int F, float* feat,
-                                           int qterm, int col0, int warp, int lane) {
+__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane) {
+  constexpr int w_off = conv_w_slot(N), b_off = conv_b_slot(N);
   constexpr int ROWS_PER_WARP = QT / (NT / 32);
   for (int r = 0; r < ROWS_PER_WARP; ++r) {
     const int qrow = warp * ROWS_PER_WARP + r;
@@ -68,9 +72,9 @@ __device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a,
       if (FT > 0) {
 #pragma unroll
         for (int f = 0; f < FT; ++f) {
-          float x = c_conv_b[b_off + f];
+          float x = fmaf(c_conv_w[w_off + f * N * N], win[0], c_conv_b[b_off + f]);
 #pragma unroll
-          for (int t = 0; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
+          for (int t = 1; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
           best = fmaxf(best, x);
         }
       } else {
@@ -107,14 +111,13 @@ __device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a,
 }
 
 template <int FT>
-__device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, int w_off, int b_off, float* feat,
-                                               int qterm, int col0, int warp, int lane) {
+__device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane) {
   switch (n) {
-    case 1: ngram_pass<1, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
-    case 2: ngram_pass<2, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
-    case 3: ngram_pass<3, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
-    case 4: ngram_pass<4, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
-    default: ngram_pass<5, FT>(s, a, w_off, b_off, a.F, feat, qterm, col0, warp, lane); break;
+    case 1: ngram_pass<1, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 2: ngram_pass<2, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 3: ngram_pass<3, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 4: ngram_pass<4, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    default: ngram_pass<5, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
   }
 }
 
@@ -128,8 +131,8 @@ __device__ __forceinline__ void pacrr_epilogue(const float* sim, const PacrrArgs
   const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
   for (int g = 0; g < ngrams; ++g) {
     const int n = a.mingram + g;
-    if (a.F == 32) ngram_dispatch<32>(n, sim, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
-    else ngram_dispatch<0>(n, sim, a, a.w_off[g], g * MAX_FILTERS, feat, qterm, g * a.kmax, warp, lane);
+    if (a.F == 32) ngram_dispatch<32>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
+    else ngram_dispatch<0>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
   }
   if (a.idf && warp == 0) {
     // softmax over the query axis of the raw idf vector, pads included (PACRR.py:47-50)
@@ -247,14 +250,12 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
   // Stage the filter taps in constant memory (stream-ordered device-to-device copies; the constant bank
   // is per device, so concurrent PACRR calls with different weights must share one stream).
-  int off = 0;
   for (int g = 0; g <= maxgram - mingram; ++g) {
     const int n = mingram + g;
     CAPR_REQUIRE(conv_w[g] && conv_b[g], CAPR_ERR_BAD_POINTER, "%s: null conv weight %d", fn, g);
-    a.w_off[g] = off;
-    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_w, conv_w[g], sizeof(float) * nfilters * n * n, sizeof(float) * off, cudaMemcpyDeviceToDevice, st));
-    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * g * MAX_FILTERS, cudaMemcpyDeviceToDevice, st));
-    off += nfilters * n * n;
+    a.w_off[g] = conv_w_slot(n);
+    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_w, conv_w[g], sizeof(float) * nfilters * n * n, sizeof(float) * conv_w_slot(n), cudaMemcpyDeviceToDevice, st));
+    CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * conv_b_slot(n), cudaMemcpyDeviceToDevice, st));
   }
   const size_t extra = (size_t)(QT * (MAX_GRAMS * MAX_KMAX + 1) + 2 * MAX_COMBINE) * sizeof(float);
   const int sms = sm_count();
