@@ -12,11 +12,12 @@
 // (fp32 FFMA flash-style, v1), pooler+classifier; the Linear layers run on tcgen05 (bert_gemm.cuh).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
 
-#include "bert_gemm.cuh"
+#include "bert_attn.cuh"
 #include "tmap.cuh"
 
 namespace capr {
@@ -332,6 +333,7 @@ struct Model {
   float *pool_w = nullptr, *pool_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
   std::vector<void*> owned;
   int sms = 0;
+  bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
 };
 
 static int dev_alloc(Model* m, void** p, size_t bytes) {
@@ -390,7 +392,7 @@ static int gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMap& a_lo
 }
 
 struct Workspace {
-  float *x, *y, *qkv;
+  float *x, *y, *qkv;  // qkv: fp32 [Tp,3H] (FFMA attention) or, aliased, two bf16 planes [Tp,3H] (tensor-core attention)
   __nv_bfloat16 *x_hi, *x_lo, *ctx_hi, *ctx_lo, *ffn_hi, *ffn_lo;
 };
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -448,6 +450,10 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
   m->cfg = *cfg;
   m->mode = precision_mode == CAPR_BERT_BF16X3 ? 3 : 1;
   m->sms = sm_count();
+  {
+    const char* e = getenv("CAPR_BERT_ATTENTION");
+    m->ffma_attention = e && e[0] == 'f';
+  }
   const size_t H = cfg->hidden, I = cfg->intermediate;
   int rc = CAPR_OK;
 #define CAPR_TRY(expr)            \
@@ -550,13 +556,37 @@ int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, co
   CAPR_CHECK_CUDA(cudaGetLastError());
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
   const int att_grid = n_seq * heads * ((L + ATT_BQ - 1) / ATT_BQ);
+  // tensor-core attention: head dim 64, L <= 512; Q/K/V then live as bf16 (hi, lo) planes aliased onto the fp32 qkv buffer
+  const bool tc_attention = dh == AT_DH && L <= AT_MAX_L && !m->ffma_attention;
+  __nv_bfloat16* qkv_hi = reinterpret_cast<__nv_bfloat16*>(ws.qkv);
+  __nv_bfloat16* qkv_lo = qkv_hi + Tp * 3 * H;
+  CUtensorMap q_hi, q_lo, kv_hi, kv_lo;
+  if (tc_attention) {
+    if ((rc = make_map(&q_hi, qkv_hi, Tp, 3 * H, AT_BQ))) return rc;
+    if ((rc = make_map(&q_lo, qkv_lo, Tp, 3 * H, AT_BQ))) return rc;
+    if ((rc = make_map(&kv_hi, qkv_hi, Tp, 3 * H, AT_BK))) return rc;
+    if ((rc = make_map(&kv_lo, qkv_lo, Tp, 3 * H, AT_BK))) return rc;
+    if (Tp > T) {  // K/V tiles may reach into the pad rows: they are multiplied by P = 0, so they must be finite
+      CAPR_CHECK_CUDA(cudaMemsetAsync(qkv_hi + T * 3 * H, 0, (Tp - T) * 3 * H * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(qkv_lo + T * 3 * H, 0, (Tp - T) * 3 * H * 2, st));
+    }
+    CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+  }
+  const AttnArgs at{L, H, heads, n_seq, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
+  const int att_tc_grid = n_seq * heads * ((L + AT_BQ - 1) / AT_BQ);
   for (int l = 0; l < m->cfg.layers; ++l) {
     const Layer& ly = m->layers[l];
-    if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;
-    if (dh == 64) rc = launch_attention<64>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
-    else if (dh == 32) rc = launch_attention<32>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
-    else rc = launch_attention<16>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
-    if (rc) return rc;
+    if (tc_attention) {
+      if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_SPLIT, nullptr, nullptr, qkv_hi, qkv_lo, st))) return rc;
+      attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
+      CAPR_CHECK_CUDA(cudaGetLastError());
+    } else {
+      if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;
+      if (dh == 64) rc = launch_attention<64>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+      else if (dh == 32) rc = launch_attention<32>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+      else rc = launch_attention<16>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
+      if (rc) return rc;
+    }
     if ((rc = gemm(m, c_hi, c_lo, ly.attn_out, Ti, EPI_BIAS_RESID_F32, ws.x, ws.y, nullptr, nullptr, st))) return rc;
     ln_kernel<<<row_blocks, 256, 0, st>>>(ws.y, Ti, H, ly.ln1_g, ly.ln1_b, m->cfg.ln_eps, ws.x, ws.x_hi, ws.x_lo);
     CAPR_CHECK_CUDA(cudaGetLastError());

@@ -34,6 +34,7 @@ enum Epilogue : int {
   EPI_BIAS_F32 = 0,         // out_f32 = acc + bias
   EPI_BIAS_GELU_SPLIT = 1,  // (out_hi, out_lo) = split_bf16(gelu_erf(acc + bias))
   EPI_BIAS_RESID_F32 = 2,   // out_f32 = acc + bias + resid
+  EPI_BIAS_SPLIT = 3,       // (out_hi, out_lo) = split_bf16(acc + bias)   (Q/K/V for the tensor-core attention)
 };
 
 struct GemmArgs {
@@ -185,13 +186,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             v[4 * i + 0] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
           }
           const size_t off = (size_t)row * g.N + col;
-          if (g.epi == EPI_BIAS_GELU_SPLIT) {
+          if (g.epi == EPI_BIAS_GELU_SPLIT || g.epi == EPI_BIAS_SPLIT) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float x0 = v[2 * i], x1 = v[2 * i + 1];
-              x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));  // erf GELU (HF "gelu")
-              x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
+              if (g.epi == EPI_BIAS_GELU_SPLIT) {
+                x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));  // erf GELU (HF "gelu")
+                x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
+              }
               __nv_bfloat16 h0, l0, h1, l1;
               split_bf16(x0, h0, l0);
               split_bf16(x1, h1, l1);
@@ -203,7 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              if (MODE == 3) pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              if (MODE == 3 || g.epi == EPI_BIAS_SPLIT) pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
             }
           } else {
             if (g.epi == EPI_BIAS_RESID_F32) {
