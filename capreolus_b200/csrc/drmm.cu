@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) drmm_tc_kernel(const DrmmAr
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
   int* cnt = reinterpret_cast<int*>(s.extra);                     // [QT][MAX_SLOTS_TC]
   float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS_TC);  // [MAX_SLOTS_TC]
   float* z = ub + MAX_SLOTS_TC;                                   // [QT]
@@ -233,7 +233,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
                                     const float* out_b, float* scores, float* hist_out, capr_stream_t stream) {
   const char* fn = "capr_drmm_forward_tc";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && nodes > 0 && nbins > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d nodes=%d nbins=%d", fn, B, Q, D, V, E, nodes, nbins);
-  CAPR_REQUIRE(pitch >= E && pitch % 64 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 64 and >= E (capr_table_pitch_bf16)", fn, pitch);
+  CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 16 and >= E (capr_table_pitch_bf16)", fn, pitch);
   CAPR_REQUIRE(hist_type >= 0 && hist_type <= 2, CAPR_ERR_BAD_SHAPE, "%s: histType should be CH, NH or LCH", fn);
   CAPR_REQUIRE(gate_type == 0 || gate_type == 1, CAPR_ERR_BAD_SHAPE, "%s: gateType should be IDF or TV", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
@@ -246,7 +246,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
              nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
              simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E}};
-  const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, (size_t)QT * MAX_SLOTS_TC * sizeof(int) + (MAX_SLOTS_TC + QT) * sizeof(float));
+  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)QT * MAX_SLOTS_TC * sizeof(int) + (MAX_SLOTS_TC + QT) * sizeof(float));
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
   float* sPart = s.extra;  // [EPI_WARPS][KT] per-warp partial features
   const uint32_t tmem_base = setup(s, tid);
 
@@ -137,11 +137,11 @@ using namespace capr;
 
 extern "C" {
 
-int capr_table_pitch_bf16(int E) { return E <= 0 ? 0 : ((E + 63) / 64) * 64; }
+int capr_table_pitch_bf16(int E) { return E <= 0 ? 0 : ((E + 15) / 16) * 16; }
 
 int capr_table_prepare_bf16(const float* emb, int V, int E, void* hi, void* lo, int pitch, capr_stream_t stream) {
   CAPR_REQUIRE(V > 0 && E > 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare_bf16: V=%d E=%d must be positive", V, E);
-  CAPR_REQUIRE(pitch >= E && pitch % 64 == 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare_bf16: pitch=%d must be a multiple of 64 and >= E=%d", pitch, E);
+  CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare_bf16: pitch=%d must be a multiple of 16 and >= E=%d", pitch, E);
   CAPR_REQUIRE(emb && hi && lo, CAPR_ERR_BAD_POINTER, "capr_table_prepare_bf16: null pointer");
   CAPR_REQUIRE((((uintptr_t)hi | (uintptr_t)lo) & 15) == 0, CAPR_ERR_BAD_POINTER, "capr_table_prepare_bf16: planes must be 16-byte aligned");
   table_prepare_bf16_kernel<<<(V + 7) / 8, 256, 0, (cudaStream_t)stream>>>(emb, V, E, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, pitch);
@@ -154,7 +154,7 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
                          const float* w2, const float* b2, int flags, float* scores, float* feats, capr_stream_t stream) {
   const char* fn = "capr_knrm_forward_tc";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && K > 0 && hidden >= 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d K=%d", fn, B, Q, D, V, E, K);
-  CAPR_REQUIRE(pitch >= E && pitch % 64 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 64 and >= E (capr_table_pitch_bf16)", fn, pitch);
+  CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 16 and >= E (capr_table_pitch_bf16)", fn, pitch);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
   CAPR_REQUIRE(D <= DT, CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d: use capr_knrm_forward (doc-tiled FFMA engine)", fn, D, DT);
   CAPR_REQUIRE(pitch <= simtc::MAX_ATOMS * simtc::ATOM_K, CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d: use capr_knrm_forward", fn, simtc::MAX_ATOMS * simtc::ATOM_K);
@@ -171,7 +171,7 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E};
   a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2, a.scores = scores, a.feats = feats;
   const int KT = K <= 11 ? 11 : 16;
-  const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, (size_t)(simtc::EPI_WARPS * KT) * sizeof(float));
+  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)(simtc::EPI_WARPS * KT) * sizeof(float));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;

@@ -55,57 +55,71 @@ __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ?
 template <int N, int FT>
 __device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane) {
   constexpr int w_off = conv_w_slot(N), b_off = conv_b_slot(N);
-  constexpr int ROWS_PER_WARP = QT / (NT / 32);
-  for (int r = 0; r < ROWS_PER_WARP; ++r) {
-    const int qrow = warp * ROWS_PER_WARP + r;
-    if (qrow >= a.Q) continue;  // warp-uniform
-    float top[MAX_KMAX];
+  constexpr int R = QT / (NT / 32);  // the 4 query rows of this warp are convolved together: every filter tap
+  const int q0 = warp * R;           // (a uniform-register operand) feeds 4 FFMAs, and the 4 windows share rows
+  if (q0 >= a.Q) return;             // warp-uniform
+  float top[R][MAX_KMAX];
 #pragma unroll
-    for (int k = 0; k < MAX_KMAX; ++k) top[k] = -INFINITY;
-    for (int c = lane; c < a.D; c += 32) {
-      float win[N * N];
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < MAX_KMAX; ++k) top[r][k] = -INFINITY;
+  for (int c = lane; c < a.D; c += 32) {
+    float win[R + N - 1][N];
+#pragma unroll
+    for (int u = 0; u < R + N - 1; ++u)
+#pragma unroll
+      for (int v = 0; v < N; ++v) win[u][v] = sim[(q0 + u) * SIM_PITCH + c + v];
+    float best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) best[r] = -INFINITY;
+    auto one_filter = [&](int f) {
+      float x[R];
+      const float bias = c_conv_b[b_off + f];
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r] = bias;
 #pragma unroll
       for (int u = 0; u < N; ++u)
 #pragma unroll
-        for (int v = 0; v < N; ++v) win[u * N + v] = sim[(qrow + u) * SIM_PITCH + c + v];
-      float best = -INFINITY;
-      if (FT > 0) {
+        for (int v = 0; v < N; ++v) {
+          const float w = c_conv_w[w_off + f * N * N + u * N + v];
 #pragma unroll
-        for (int f = 0; f < FT; ++f) {
-          float x = fmaf(c_conv_w[w_off + f * N * N], win[0], c_conv_b[b_off + f]);
-#pragma unroll
-          for (int t = 1; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
-          best = fmaxf(best, x);
+          for (int r = 0; r < R; ++r) x[r] = fmaf(w, win[r + u][v], x[r]);
         }
-      } else {
-        for (int f = 0; f < F; ++f) {
-          float x = c_conv_b[b_off + f];
 #pragma unroll
-          for (int t = 0; t < N * N; ++t) x = fmaf(c_conv_w[w_off + f * N * N + t], win[t], x);
-          best = fmaxf(best, x);
-        }
-      }
-      best = fmaxf(best, 0.f);  // ReLU (PACRR.py:78) commutes with the filter max (PACRR.py:79)
-      // insert into the lane-local descending top-k
+      for (int r = 0; r < R; ++r) best[r] = fmaxf(best[r], x[r]);
+    };
+    if (FT > 0) {
 #pragma unroll
-      for (int k = 0; k < MAX_KMAX; ++k) {
-        if (k < a.kmax && best > top[k]) {
-          const float t = top[k];
-          top[k] = best;
-          best = t;
+      for (int f = 0; f < FT; ++f) one_filter(f);
+    } else {
+      for (int f = 0; f < F; ++f) one_filter(f);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v = fmaxf(best[r], 0.f);  // ReLU (PACRR.py:78) commutes with the filter max (PACRR.py:79)
+#pragma unroll
+      for (int k = 0; k < MAX_KMAX; ++k) {  // insert into the lane-local descending top-k
+        if (k < a.kmax && v > top[r][k]) {
+          const float t = top[r][k];
+          top[r][k] = v;
+          v = t;
         }
       }
     }
-    // merge the 32 lane-local lists: kmax rounds of (warp max, owner pops its head)
+  }
+  // merge the 32 lane-local lists of every row: kmax rounds of (warp max, owner pops its head)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (q0 + r >= a.Q) break;  // warp-uniform
     for (int k = 0; k < a.kmax; ++k) {
-      const float m = warp_max(top[0]);
-      const unsigned owners = __ballot_sync(0xffffffffu, top[0] == m);
+      const float m = warp_max(top[r][0]);
+      const unsigned owners = __ballot_sync(0xffffffffu, top[r][0] == m);
       if (lane == (__ffs(owners) - 1)) {
 #pragma unroll
-        for (int j = 0; j < MAX_KMAX - 1; ++j) top[j] = top[j + 1];
-        top[MAX_KMAX - 1] = -INFINITY;
+        for (int j = 0; j < MAX_KMAX - 1; ++j) top[r][j] = top[r][j + 1];
+        top[r][MAX_KMAX - 1] = -INFINITY;
       }
-      if (lane == 0) feat[qrow * qterm + col0 + k] = m;
+      if (lane == 0) feat[(q0 + r) * qterm + col0 + k] = m;
     }
   }
 }
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, a.pr.pitch / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
   float* feat = s.extra;
   float* h1 = feat + QT * (MAX_GRAMS * MAX_KMAX + 1);
   float* h2 = h1 + MAX_COMBINE;
@@ -231,7 +245,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d", fn, B, Q, D, V);
   CAPR_REQUIRE(mingram >= 1 && maxgram >= mingram && nfilters > 0 && kmax > 0 && combine > 0, CAPR_ERR_BAD_SHAPE, "%s: bad config mingram=%d maxgram=%d nfilters=%d kmax=%d combine=%d", fn, mingram, maxgram, nfilters, kmax, combine);
   CAPR_REQUIRE(nonlin >= 0 && nonlin <= 2, CAPR_ERR_BAD_SHAPE, "%s: nonlinearity must be none, relu or tanh", fn);
-  CAPR_REQUIRE(pitch > 0 && pitch % (tc_engine ? 64 : 16) == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of %d", fn, pitch, tc_engine ? 64 : 16);
+  CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16", fn, pitch);
   CAPR_REQUIRE(B == 0 || (query && doc && table && (!tc_engine || table_lo) && conv_w && conv_b && l1w && l1b && l2w && l2b && l3w && l3b && scores), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
@@ -261,7 +275,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   if (tc_engine) {
-    const size_t smem = simtc::smem_bytes(pitch / simtc::ATOM_K, extra);
+    const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, extra);
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pacrr_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
   } else {

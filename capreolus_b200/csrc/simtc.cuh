@@ -85,7 +85,7 @@ struct Problem {
   int B, Q, D, V;
   const __nv_bfloat16* hi;  // [V][pitch]
   const __nv_bfloat16* lo;
-  int pitch;                // elements, multiple of 64
+  int pitch;                // elements per table row, multiple of 16 (the last 64-element K atom may be partial)
   int E;
 };
 
@@ -136,7 +136,8 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 __device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
 __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, int ptid /*0..127*/) {
-  const int atoms = pr.pitch / ATOM_K;
+  const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
+  const int last_chunks = (pr.pitch - (atoms - 1) * ATOM_K) / 8;  // 16-byte chunks that exist in the last atom
   const int n_mt = (pr.D + MT - 1) / MT;
   const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
   const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
@@ -159,7 +160,8 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
         const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[r & 31] * pr.pitch + sub * 8;
         const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
         for (int a = 0; a < atoms; ++a)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
+          if (a + 1 < atoms || sub < last_chunks)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
       }
     }
     cp_async_arrive_noinc(&s.q_full[b]);
@@ -173,10 +175,12 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
           const uint32_t base = tc::smem_u32(s.d[d_stage]);
+          if (a + 1 < atoms || sub < last_chunks) {  // the tail chunks of a partial last atom are never read by the MMAs
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = rsub + 16 * j;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
+            for (int j = 0; j < 8; ++j) {
+              const int r = rsub + 16 * j;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
+            }
           }
           cp_async_arrive_noinc(&s.d_full[d_stage]);
           if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
@@ -190,7 +194,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 
 // ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint32_t tmem_base) {
-  const int atoms = pr.pitch / ATOM_K;
+  const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int n_mt = (pr.D + MT - 1) / MT;
   const uint32_t idesc64 = tc::make_instr_desc(tc::FMT_BF16, MT, 64);
   const uint32_t idesc32 = tc::make_instr_desc(tc::FMT_BF16, MT, 32);
@@ -208,7 +212,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT);
       for (int a = 0; a < atoms; ++a) {
         const uint64_t bq = tc::make_sw128_kmajor_desc(qaddr + a * Q_ATOM_BYTES);
-        const int ksteps = min(ATOM_K, pr.E - a * ATOM_K + 15) / 16;  // skip the all-zero tail of the last atom
+        const int ksteps = min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           tc::mbar_wait(&s.d_full[d_stage], d_phase);

@@ -80,7 +80,7 @@ int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, in
 
 /* Engine 2 (tensor cores): same contract as capr_knrm_forward (inference outputs only), but the cosine tile is
  * computed by tcgen05.mma from a table stored as two bf16 planes, hi = bf16(e) and lo = bf16(e - hi) of the same
- * L2-normalised rows (capr_table_prepare_bf16; pitch = capr_table_pitch_bf16(E), a multiple of 64 elements), with
+ * L2-normalised rows (capr_table_prepare_bf16; pitch = capr_table_pitch_bf16(E), E rounded up to a multiple of 16), with
  * the three products hi.hi + hi.lo + lo.hi accumulated in fp32.  Limits: D <= 512, pitch <= 320, K <= 16 (else
  * CAPR_ERR_UNSUPPORTED -> use capr_knrm_forward). */
 int capr_table_pitch_bf16(int E);
