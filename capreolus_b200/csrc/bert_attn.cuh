@@ -111,28 +111,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
   const int col_q = head * AT_DH, col_k = a.H + head * AT_DH, col_v = 2 * a.H + head * AT_DH;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(q_full, 2 * AT_Q_BYTES);
       tc::tma_load_2d(sQ, &tm_q_hi, q_full, col_q, tok0 + qb * AT_BQ);
       tc::tma_load_2d(sQ + AT_Q_BYTES, &tm_q_lo, q_full, col_q, tok0 + qb * AT_BQ);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        tc::mbar_wait(&kv_empty[stage], phase ^ 1);
-        unsigned char* st = sKV + stage * AT_KV_STAGE_BYTES;
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      tc::mbar_wait(&kv_empty[stage], phase ^ 1);
+      unsigned char* st = sKV + stage * AT_KV_STAGE_BYTES;
+      const int row = tok0 + t * AT_BK;
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&kv_full[stage], AT_KV_STAGE_BYTES);
-        const int row = tok0 + t * AT_BK;
         tc::tma_load_2d(st, &tm_kv_hi, &kv_full[stage], col_k, row);
         tc::tma_load_2d(st + AT_T_BYTES, &tm_kv_lo, &kv_full[stage], col_k, row);
         tc::tma_load_2d(st + 2 * AT_T_BYTES, &tm_kv_hi, &kv_full[stage], col_v, row);
         tc::tma_load_2d(st + 3 * AT_T_BYTES, &tm_kv_lo, &kv_full[stage], col_v, row);
-        if (++stage == AT_KV_STAGES) stage = 0, phase ^= 1;
       }
+      __syncwarp();
+      if (++stage == AT_KV_STAGES) stage = 0, phase ^= 1;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && n_tiles > 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    if (n_tiles > 0) {
       const uint32_t idesc_qk = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_BK);
       const uint32_t idesc_pv = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_DH) | (1u << 16);  // B is MN-major (V: dims contiguous)
       const uint32_t q_hi = tc::smem_u32(sQ), q_lo = q_hi + AT_Q_BYTES;
@@ -144,14 +148,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         tc::tc_fence_after();
         const uint32_t k_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES), k_lo = k_hi + AT_T_BYTES;
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * AT_BK);
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k) {
-          const uint32_t ko = k * 32;
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, k != 0);
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_lo + ko), idesc_qk, true);
+          for (int k = 0; k < AT_DH / 16; ++k) {
+            const uint32_t ko = k * 32;
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, k != 0);
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_lo + ko), idesc_qk, true);
+          }
+          tc::umma_commit(&s_full[buf]);
         }
-        tc::umma_commit(&s_full[buf]);
+        __syncwarp();
       };
       auto issue_pv = [&](int t) {
         const int stage = t % AT_KV_STAGES, buf = t & 1;
@@ -161,17 +168,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_co
         const uint32_t v_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES + 2 * AT_T_BYTES), v_lo = v_hi + AT_T_BYTES;
         const uint32_t p_hi = tc::smem_u32(sP + buf * 2 * AT_P_BYTES), p_lo = p_hi + AT_P_BYTES;
         const uint32_t d_tmem = tmem_base + (uint32_t)(128 + buf * AT_DH);
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          const uint32_t pk = k * 32;           // 16 keys = 32 bytes along P's K-major rows
-          const uint32_t vk = k * 16 * 128;     // 16 keys = 16 rows of the V tile
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, k != 0);
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_lo + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, true);
-          tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_lo + vk), idesc_pv, true);
+          for (int k = 0; k < AT_BK / 16; ++k) {
+            const uint32_t pk = k * 32;           // 16 keys = 32 bytes along P's K-major rows
+            const uint32_t vk = k * 16 * 128;     // 16 keys = 16 rows of the V tile
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, k != 0);
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_lo + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, true);
+            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_lo + vk), idesc_pv, true);
+          }
+          tc::umma_commit(&o_full[buf]);
+          tc::umma_commit(&kv_empty[stage]);
+          tc::umma_commit(&p_empty[buf]);
         }
-        tc::umma_commit(&o_full[buf]);
-        tc::umma_commit(&kv_empty[stage]);
-        tc::umma_commit(&p_empty[buf]);
+        __syncwarp();
       };
       issue_qk(0);
       for (int t = 0; t < n_tiles; ++t) {

@@ -106,7 +106,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       const uint32_t stage_tx = (uint32_t)S::PLANES * (uint32_t)(A_TILE_BYTES + g.BN * BK * 2);
       int stage = 0;
       uint32_t phase = 0;
@@ -115,20 +115,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + stage * S::STAGE_BYTES;
-          tc::mbar_expect_tx(&full[stage], stage_tx);
-          tc::tma_load_2d(st, &tm_a_hi, &full[stage], kb * BK, m0);
-          tc::tma_load_2d(st + A_TILE_BYTES, &tm_b_hi, &full[stage], kb * BK, n0);
-          if (MODE == 3) {
-            tc::tma_load_2d(st + A_TILE_BYTES + B_TILE_BYTES, &tm_a_lo, &full[stage], kb * BK, m0);
-            tc::tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &full[stage], kb * BK, n0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full[stage], stage_tx);
+            tc::tma_load_2d(st, &tm_a_hi, &full[stage], kb * BK, m0);
+            tc::tma_load_2d(st + A_TILE_BYTES, &tm_b_hi, &full[stage], kb * BK, n0);
+            if (MODE == 3) {
+              tc::tma_load_2d(st + A_TILE_BYTES + B_TILE_BYTES, &tm_a_lo, &full[stage], kb * BK, m0);
+              tc::tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &full[stage], kb * BK, n0);
+            }
           }
+          __syncwarp();
           if (++stage == S::STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop and one elected lane issues: with warp-uniform control flow ptxas keeps the
+    // descriptors in uniform registers (a divergent `if (lane == 0)` issuer costs ~150 cycles per tcgen05.mma).
+    {
       const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, BM, g.BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -146,19 +151,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           const uint64_t b_hi = tc::make_sw128_kmajor_desc(st + A_TILE_BYTES);
           const uint64_t a_lo = tc::make_sw128_kmajor_desc(st + A_TILE_BYTES + B_TILE_BYTES);
           const uint64_t b_lo = tc::make_sw128_kmajor_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per K=16 step, in 16-byte units
-            tc::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
-            if (MODE == 3) {
-              tc::umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, true);
-              tc::umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, true);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per K=16 step, in 16-byte units
+              tc::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+              if (MODE == 3) {
+                tc::umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, true);
+                tc::umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, true);
+              }
             }
+            tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
           }
-          tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == S::STAGES) stage = 0, phase ^= 1;
         }
-        tc::umma_commit(&acc_full[acc]);  // accumulator complete
+        if (tc::elect_one()) tc::umma_commit(&acc_full[acc]);  // accumulator complete
+        __syncwarp();
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
     }

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) drmm_tc_kernel(const DrmmAr
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
-    if (lane == 0) mma_loop(s, a.pr, tmem_base);
+    mma_loop(s, a.pr, tmem_base);
   } else {
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
@@ -245,7 +245,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   CAPR_REQUIRE(gate_type != CAPR_DRMM_GATE_TV || raw_emb, CAPR_ERR_BAD_POINTER, "%s: TV gate needs the raw embedding table", fn);
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
              nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
-             simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E}};
+             simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}};
   const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)QT * MAX_SLOTS_TC * sizeof(int) + (MAX_SLOTS_TC + QT) * sizeof(float));
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();

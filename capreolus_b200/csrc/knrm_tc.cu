@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
-    if (lane == 0) mma_loop(s, a.pr, tmem_base);
+    mma_loop(s, a.pr, tmem_base);
   } else {
     // ===================== epilogue: 8 warps, 4 query rows each =====================
     float mu[KT], cc[KT];
@@ -168,7 +168,7 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
     CAPR_REQUIRE(hidden == 0 || (w2 && b2), CAPR_ERR_BAD_POINTER, "%s: hidden=%d needs w2/b2", fn, hidden);
   }
   KnrmTcArgs a{};
-  a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E};
+  a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, flags & 0xF00};
   a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2, a.scores = scores, a.feats = feats;
   const int KT = K <= 11 ? 11 : 16;
   const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)(simtc::EPI_WARPS * KT) * sizeof(float));

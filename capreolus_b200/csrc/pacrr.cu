@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
-    if (lane == 0) mma_loop(s, a.pr, tmem_base);
+    mma_loop(s, a.pr, tmem_base);
   } else {
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
@@ -260,7 +260,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   a.q = (const long long*)query; a.d = (const long long*)doc; a.idf = idf;
   a.B = B; a.Q = Q; a.D = D; a.V = V; a.pitch = pitch; a.mingram = mingram; a.maxgram = maxgram; a.F = nfilters;
   a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = tc_engine ? nullptr : (const float*)table;
-  if (tc_engine) a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E};
+  if (tc_engine) a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E, 0};
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
   // Stage the filter taps in constant memory (stream-ordered device-to-device copies; the constant bank
   // is per device, so concurrent PACRR calls with different weights must share one stream).

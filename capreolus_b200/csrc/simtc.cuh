@@ -87,6 +87,7 @@ struct Problem {
   const __nv_bfloat16* lo;
   int pitch;                // elements per table row, multiple of 16 (the last 64-element K atom may be partial)
   int E;
+  int debug;                // CAPR_DEBUG_* profiling switches (0 in production)
 };
 
 // Common prologue: barriers + TMEM.  Call from all threads; returns the TMEM base.
@@ -175,7 +176,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
           const uint32_t base = tc::smem_u32(s.d[d_stage]);
-          if (a + 1 < atoms || sub < last_chunks) {  // the tail chunks of a partial last atom are never read by the MMAs
+          if ((a + 1 < atoms || sub < last_chunks) && !(pr.debug & 0x800)) {  // the tail chunks of a partial last atom are never read by the MMAs
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int r = rsub + 16 * j;
@@ -192,12 +193,16 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   cp_async_wait<0>();  // nothing may still be landing in shared memory when the CTA tears down
 }
 
-// ---- MMA issuer (one thread) ------------------------------------------------------------------------------------------
+// ---- MMA issuer: the WHOLE warp runs the loop (waits are warp-wide), one elected lane issues ----------------------------
+// Keeping the control flow warp-uniform lets ptxas hold descriptors / addresses in uniform registers; issuing from a
+// divergent `if (lane == 0)` region instead costs ~150 cycles per tcgen05.mma (R2UR chains + a serialising
+// ELECT/BRA.U.ANY loop around every UTCHMMA), which capped the first version of this kernel at 8.5 M pairs/s.
 __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint32_t tmem_base) {
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int n_mt = (pr.D + MT - 1) / MT;
   const uint32_t idesc64 = tc::make_instr_desc(tc::FMT_BF16, MT, 64);
   const uint32_t idesc32 = tc::make_instr_desc(tc::FMT_BF16, MT, 32);
+  const bool skip = (pr.debug & 0x400) != 0;
   uint32_t q_phase[2] = {0, 0}, acc_phase[2] = {0, 0}, d_phase = 0;
   int d_stage = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
@@ -207,29 +212,35 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
     tc::mbar_wait(&s.q_full[b], q_phase[b]);
     q_phase[b] ^= 1;
     tc::tc_fence_after();
-    const uint32_t qaddr = tc::smem_u32(s.q[b]);
+    const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.q[b]));
     for (int mt = 0; mt < n_mt; ++mt) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT);
       for (int a = 0; a < atoms; ++a) {
-        const uint64_t bq = tc::make_sw128_kmajor_desc(qaddr + a * Q_ATOM_BYTES);
-        const int ksteps = min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
+        const uint64_t bq = q_desc + (uint64_t)((a * Q_ATOM_BYTES) >> 4);
+        const int ksteps = skip ? 0 : min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           tc::mbar_wait(&s.d_full[d_stage], d_phase);
           tc::tc_fence_after();
           const uint64_t ad = tc::make_sw128_kmajor_desc(tc::smem_u32(s.d[d_stage]));
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
-            if (plane == 0) tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc64, (a | k) != 0);  // [d_hi.q_hi | d_hi.q_lo]
-            else tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc32, true);                      //  += d_lo.q_hi
+          if (tc::elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
+              if (plane == 0) tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc64, (a | k) != 0);  // [d_hi.q_hi | d_hi.q_lo]
+              else tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc32, true);                      //  += d_lo.q_hi
+            }
+            tc::umma_commit(&s.d_empty[d_stage]);
           }
-          tc::umma_commit(&s.d_empty[d_stage]);
+          __syncwarp();
           if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
         }
       }
     }
-    tc::umma_commit(&s.q_empty[b]);
-    tc::umma_commit(&s.acc_full[b]);
+    if (tc::elect_one()) {
+      tc::umma_commit(&s.q_empty[b]);
+      tc::umma_commit(&s.acc_full[b]);
+    }
+    __syncwarp();
   }
 }
 

@@ -73,6 +73,8 @@ int capr_simmat_forward(const int64_t* query, const int64_t* doc, int B, int Q, 
 /* profiling aids for capr_knrm_forward_tc only (results are NOT valid when set): skip the pooling loop / the TMEM drain */
 #define CAPR_DEBUG_SKIP_POOL 0x100
 #define CAPR_DEBUG_SKIP_DRAIN 0x200
+#define CAPR_DEBUG_SKIP_MMA 0x400
+#define CAPR_DEBUG_SKIP_GATHER 0x800
 int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
                       int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1,
                       int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
@@ -176,6 +178,10 @@ int capr_bert_forward(capr_bert_t handle, const int64_t* ids, const int64_t* mas
 /* Test hook: C[M,N] = A[M,K] . W[N,K]^T + bias through the encoder's tcgen05 GEMM kernel (synchronises the stream). */
 int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c,
                    capr_stream_t stream);
+
+/* Debug micro-benchmark (not on any product path): cycles[grid] = best-of-reps SM cycles for n_mma back-to-back
+ * tcgen05.mma of shape M x N x 16 (bf16, shared-memory operands) cycling over n_acc accumulators. */
+int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps, int grid, long long* cycles, capr_stream_t stream);
 
 #ifdef __cplusplus
 }
