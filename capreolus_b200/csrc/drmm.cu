@@ -59,16 +59,26 @@ __device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid
       const long long did = c < ncols ? dids[c] : 0;
       const bool real = did != 0;  // padded columns are pushed to +1e7: no bin (DRMM.py:59)
       const float v = real ? row[c] : 0.f;
+      // bin = the smallest i with v < ub[i]: an arithmetic guess corrected by one against the exact fp32 bounds
       int b = (int)floorf((v + 1.0f) * guess_scale);
-      b = max(0, min(b, a.nbins));
-      while (b < a.nbins && !(v < ub[b])) ++b;
-      while (b > 0 && v < ub[b - 1]) --b;
+      b = max(0, min(b, a.nbins - 1));
+      b += (v >= ub[b]) ? 1 : 0;                       // ub[nbins-1] = 1.0: v >= 1 -> b = nbins = "no bin"
+      b -= (b > 0 && b <= a.nbins && v < ub[b - 1]) ? 1 : 0;
+      b -= (b > 0 && v < ub[b - 1]) ? 1 : 0;           // the guess can be off by one more after rounding
+      b += (b < a.nbins && v >= ub[b]) ? 1 : 0;
       // identical in-vocabulary tokens are stored as exactly 1.0f (simtile.cuh); their exact-arithmetic cosine
       // 1 - 2e-9/|a| is < 1.0, i.e. inside the last regular bin [ub[nbins-2], 1.0) as well as the exact slot
       if (real && v == 1.0f && qi > 0 && (long long)qi == did) b = a.nbins - 1;
-      if (!real) b = a.nbins + 1;  // sentinel group, never stored
-      const unsigned peers = __match_any_sync(0xffffffffu, b);
-      if (b < a.nbins && lane == (__ffs(peers) - 1)) c_row[b] += __popc(peers);
+      if (!real) b = a.nbins;  // padded columns: no bin
+      // count: peel off one distinct bin per round (typically 2-4 rounds; cosines of unrelated terms cluster around 0)
+      unsigned todo = __ballot_sync(0xffffffffu, b < a.nbins);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lb = __shfl_sync(0xffffffffu, b, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, b == lb);
+        if (lane == leader) c_row[lb] += __popc(same);
+        todo &= ~same;
+      }
       const unsigned exact = __ballot_sync(0xffffffffu, real && v > 0.999f && v < 1.001f);  // DRMM.py:66
       if (lane == 0 && exact) c_row[a.nbins] += __popc(exact);
       __syncwarp();
