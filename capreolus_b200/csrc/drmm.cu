@@ -49,36 +49,38 @@ template <int SLOTS>
 __device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid, const long long* __restrict__ dids, int ncols,
                                                 const DrmmArgs& a, const float* ub, int* cnt, int warp, int lane) {
   const float guess_scale = 0.5f * (float)a.nbins;
+  // this lane's doc ids (columns lane, lane+32, ...), fetched once for the 4 query rows of the warp
+  int dd[DT / 32];
+#pragma unroll
+  for (int t = 0; t < DT / 32; ++t) {
+    const int c = lane + 32 * t;
+    dd[t] = c < ncols ? id_as_int(dids[c]) : 0;
+  }
   for (int r = 0; r < 4; ++r) {
     const int qrow = warp * 4 + r;
     const float* row = sim + qrow * SIM_PITCH;
     int* c_row = cnt + qrow * SLOTS;
     const int qi = qid[qrow];
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      const int c = c0 + lane;
-      const long long did = c < ncols ? dids[c] : 0;
+#pragma unroll
+    for (int t = 0; t < DT / 32; ++t) {
+      if (t * 32 >= ncols) break;  // warp-uniform
+      const int c = lane + 32 * t;
+      const int did = dd[t];
       const bool real = did != 0;  // padded columns are pushed to +1e7: no bin (DRMM.py:59)
       const float v = real ? row[c] : 0.f;
-      // bin = the smallest i with v < ub[i]: an arithmetic guess corrected by one against the exact fp32 bounds
-      int b = (int)floorf((v + 1.0f) * guess_scale);
-      b = max(0, min(b, a.nbins - 1));
-      b += (v >= ub[b]) ? 1 : 0;                       // ub[nbins-1] = 1.0: v >= 1 -> b = nbins = "no bin"
-      b -= (b > 0 && b <= a.nbins && v < ub[b - 1]) ? 1 : 0;
-      b -= (b > 0 && v < ub[b - 1]) ? 1 : 0;           // the guess can be off by one more after rounding
-      b += (b < a.nbins && v >= ub[b]) ? 1 : 0;
+      // bin = the smallest i with v < ub[i].  The bounds are torch.linspace(-1,1,nbins+1)[1:], so the arithmetic guess
+      // is off by at most one (only when v sits within rounding of an edge); one comparison on each side against the
+      // exact fp32 bounds settles it.  v >= ub[nbins-1] = 1.0 -> nbins = "no bin".
+      const int g = max(0, min((int)floorf((v + 1.0f) * guess_scale), a.nbins - 1));
+      const float hi = ub[g];
+      const float lo = ub[max(g - 1, 0)];
+      int b = g + ((v >= hi) ? 1 : 0) - ((g > 0 && v < lo) ? 1 : 0);
       // identical in-vocabulary tokens are stored as exactly 1.0f (simtile.cuh); their exact-arithmetic cosine
       // 1 - 2e-9/|a| is < 1.0, i.e. inside the last regular bin [ub[nbins-2], 1.0) as well as the exact slot
-      if (real && v == 1.0f && qi > 0 && (long long)qi == did) b = a.nbins - 1;
-      if (!real) b = a.nbins;  // padded columns: no bin
-      // count: peel off one distinct bin per round (typically 2-4 rounds; cosines of unrelated terms cluster around 0)
-      unsigned todo = __ballot_sync(0xffffffffu, b < a.nbins);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int lb = __shfl_sync(0xffffffffu, b, leader);
-        const unsigned same = __ballot_sync(0xffffffffu, b == lb);
-        if (lane == leader) c_row[lb] += __popc(same);
-        todo &= ~same;
-      }
+      if (real && v == 1.0f && qi > 0 && qi == did) b = a.nbins - 1;
+      if (!real) b = a.nbins + 1;  // sentinel group, never stored
+      const unsigned peers = __match_any_sync(0xffffffffu, b);
+      if (b < a.nbins && lane == (__ffs(peers) - 1)) c_row[b] += __popc(peers);
       const unsigned exact = __ballot_sync(0xffffffffu, real && v > 0.999f && v < 1.001f);  // DRMM.py:66
       if (lane == 0 && exact) c_row[a.nbins] += __popc(exact);
       __syncwarp();
