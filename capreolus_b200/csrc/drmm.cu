@@ -46,15 +46,15 @@ struct EpiSync {
 
 // Bin the `ncols` cosines of every query row of the tile (8 warps x 4 rows).  `dids` = the doc ids of these columns.
 template <int SLOTS>
-__device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid, const long long* __restrict__ dids, int ncols,
-                                                const DrmmArgs& a, const float* ub, int* cnt, int warp, int lane) {
+__device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid, const int* did_smem, int ncols, const DrmmArgs& a,
+                                                const float* ub, int* cnt, int warp, int lane) {
   const float guess_scale = 0.5f * (float)a.nbins;
   // this lane's doc ids (columns lane, lane+32, ...), fetched once for the 4 query rows of the warp
   int dd[DT / 32];
 #pragma unroll
   for (int t = 0; t < DT / 32; ++t) {
     const int c = lane + 32 * t;
-    dd[t] = c < ncols ? id_as_int(dids[c]) : 0;
+    dd[t] = c < ncols ? did_smem[c] : 0;
   }
   for (int r = 0; r < 4; ++r) {
     const int qrow = warp * 4 + r;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
     const long long* dids = a.d + (size_t)pair * a.D;
     for (int d0 = 0; d0 < a.D; d0 += DT) {
       build_sim_tile(s, a.table, a.pitch, a.V, qids, a.Q, dids, d0, a.D, d0 == 0, tid);  // also orders the cnt reset
-      drmm_count_tile<MAX_SLOTS>(s.sim, s.qid, dids + d0, min(DT, a.D - d0), a, ub, cnt, warp, lane);
+      drmm_count_tile<MAX_SLOTS>(s.sim, s.qid, s.did, min(DT, a.D - d0), a, ub, cnt, warp, lane);
       __syncthreads();
     }
     drmm_finish<MAX_SLOTS>(a, pair, cnt, z, warp, lane, BlockSync());
@@ -188,13 +188,11 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) drmm_tc_kernel(const DrmmAr
     mma_loop(s, a.pr, tmem_base);
   } else {
     uint32_t acc_phase[2] = {0, 0};
-    int it = 0;
-    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
-      const int b = it & 1;
+    int unit = 0;
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
       for (int i = tid; i < QT * MAX_SLOTS_TC; i += EPI_THREADS) cnt[i] = 0;  // ordered by drain_pair's barriers
-      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid);
-      acc_phase[b] ^= 1;
-      drmm_count_tile<MAX_SLOTS_TC>(s.sim, s.qid, a.d + (size_t)pair * a.D, a.D, a, ub, cnt, warp, lane);
+      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);
+      drmm_count_tile<MAX_SLOTS_TC>(s.sim, s.qid, s.did, a.D, a, ub, cnt, warp, lane);
       epi_barrier();
       drmm_finish<MAX_SLOTS_TC>(a, pair, cnt, z, warp, lane, EpiSync());
       epi_barrier();
@@ -251,6 +249,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
   CAPR_REQUIRE(D <= DT && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K && nbins + 1 <= MAX_SLOTS_TC, CAPR_ERR_UNSUPPORTED,
                "%s: needs maxdoclen <= %d, emb dim <= %d, nbins <= %d: use capr_drmm_forward", fn, DT, simtc::MAX_ATOMS * simtc::ATOM_K, MAX_SLOTS_TC - 1);
+  CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table of %d x %d elements is too large for 32-bit row offsets", fn, V, pitch);
   if (B == 0) return CAPR_OK;
   CAPR_REQUIRE(query && doc && table_hi && table_lo && bin_ub && ffw_w1 && ffw_b1 && ffw_w2 && ffw_b2 && gate_w && out_w && out_b && scores, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(gate_type != CAPR_DRMM_GATE_IDF || idf, CAPR_ERR_BAD_POINTER, "%s: IDF gate needs idf", fn);

@@ -46,11 +46,9 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
     }
     constexpr int ROWS_PER_WARP = QT / EPI_WARPS;  // 4
     uint32_t acc_phase[2] = {0, 0};
-    int it = 0;
-    for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, ++it) {
-      const int b = it & 1;
-      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid, (a.flags & CAPR_DEBUG_SKIP_DRAIN) != 0);
-      acc_phase[b] ^= 1;
+    int unit = 0;
+    for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, unit += halves_of(a.pr)) {
+      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid, (a.flags & CAPR_DEBUG_SKIP_DRAIN) != 0);
       // lane k accumulates this warp's share of R_k = sum over its live rows of log(S_k + 1e-6)   (KNRM.py:50-53)
       float R_part = 0.f;
       if (!(a.flags & CAPR_DEBUG_SKIP_POOL)) {
@@ -159,6 +157,7 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   CAPR_REQUIRE(D <= DT, CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d: use capr_knrm_forward (doc-tiled FFMA engine)", fn, D, DT);
   CAPR_REQUIRE(pitch <= simtc::MAX_ATOMS * simtc::ATOM_K, CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d: use capr_knrm_forward", fn, simtc::MAX_ATOMS * simtc::ATOM_K);
   CAPR_REQUIRE(K <= 16, CAPR_ERR_UNSUPPORTED, "%s: K=%d > 16 kernels: use capr_knrm_forward", fn, K);
+  CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table of %d x %d elements is too large for 32-bit row offsets", fn, V, pitch);
   if (B == 0) return CAPR_OK;
   CAPR_REQUIRE(query && doc && table_hi && table_lo && mu && sigma, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE((((uintptr_t)table_hi | (uintptr_t)table_lo) & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table planes must be 16-byte aligned", fn);

@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
-  float* feat = s.extra;
-  float* h1 = feat + QT * (MAX_GRAMS * MAX_KMAX + 1);
+  float* feat = s.extra;  // [QT][qterm]
+  float* h1 = feat + QT * ((a.maxgram - a.mingram + 1) * a.kmax + (a.idf ? 1 : 0));
   float* h2 = h1 + MAX_COMBINE;
   const uint32_t tmem_base = setup(s, tid);
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
@@ -222,11 +222,9 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
     mma_loop(s, a.pr, tmem_base);
   } else {
     uint32_t acc_phase[2] = {0, 0};
-    int it = 0;
-    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
-      const int b = it & 1;
-      drain_pair(s, a.pr, tmem_base, pair, b, acc_phase[b], tid);
-      acc_phase[b] ^= 1;
+    int unit = 0;
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
+      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);
       pacrr_epilogue(s.sim, a, pair, feat, h1, h2, tid, EpiSync());
     }
   }
@@ -272,10 +270,13 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
     CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * conv_b_slot(n), cudaMemcpyDeviceToDevice, st));
   }
   const size_t extra = (size_t)(QT * (MAX_GRAMS * MAX_KMAX + 1) + 2 * MAX_COMBINE) * sizeof(float);
+  const size_t extra_tc = (size_t)(QT * ((maxgram - mingram + 1) * kmax + (idf ? 1 : 0)) + 2 * MAX_COMBINE) * sizeof(float);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   if (tc_engine) {
-    const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, extra);
+    const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, extra_tc);
+    CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: ngrams*kmax too large for the tensor-core engine's shared memory: use capr_pacrr_forward", fn);
+    CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit row offsets", fn);
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pacrr_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
   } else {

@@ -2,23 +2,26 @@
 //
 //   SimilarityMatrix.forward      capreolus/reranker/common.py:170-182   (the a_emb.bmm(b_emb^T) of l.165)
 //
-// The cosine tile of one pair is a skinny GEMM: 512 doc rows x 32 query rows x E=300.  fp32 FFMA makes it the
+// The cosine tile of one pair is a skinny GEMM: 32 query rows x 512 doc rows x E=300.  fp32 FFMA makes it the
 // limiter of the whole kernel (profiles/r01_v1_*: FMA pipe 41 %, issue-bound).  Here it runs on tcgen05 instead:
 //   * the prepared table is stored as two bf16 planes, hi = bf16(e), lo = bf16(e - hi) (16 mantissa bits together),
-//     row pitch padded to a multiple of 64 elements, so a gathered row is the same 1.2 KB as in fp32;
-//   * docs are the M=128 operand (4 M-tiles per 512-doc tile), the query block is the N operand: the B tile stacks
-//     [q_hi (32 rows); q_lo (32 rows)], so one MMA with N=64 yields d_hi.q_hi (columns 0-31) and d_hi.q_lo (columns
-//     32-63), and a second MMA with N=32 adds d_lo.q_hi into columns 0-31.  cos = col[i] + col[32+i]: the three
-//     products of the (hi+lo)(hi+lo) expansion, the dropped lo.lo term is ~2^-18 relative.  CPU emulation of this
-//     arithmetic against the goldens: KNRM 8e-7, PACRR 2e-5, DRMM 0 bin flips (tests/emulate.py);
+//     row pitch = E rounded up to 16 elements, so a gathered row is the same 1.2 KB as in fp32;
+//   * the QUERY block is the M operand: A = [q_hi (rows 0-31); q_lo (rows 32-63)] (the MMA is issued with M = 128; rows
+//     64-127 read whatever follows in shared memory and produce accumulator rows nobody reads), 256 DOC rows are the N
+//     operand.  Per K step two MMAs: B = d_hi gives rows 0-31 = q_hi.d_hi and rows 32-63 = q_lo.d_hi, B = d_lo adds
+//     q_hi.d_lo to rows 0-31 (and the negligible q_lo.d_lo to rows 32-63).  cos[i][d] = D[i][d] + D[32+i][d].
+//     (A tcgen05.mma with shared-memory operands costs >= ~128 cycles whatever N is -- measured -- so the first
+//     orientation of this kernel, docs as M=128 and the query block as N=64/32, needed 152 MMAs per pair and was
+//     MMA-chain bound at 11 M pairs/s; N=256 needs 76.)  CPU emulation of the three-product arithmetic against the
+//     goldens: KNRM 8e-7, PACRR 2e-5, DRMM 0 bin flips (tests/emulate.py);
 //   * rows are gathered with 16-byte cp.async straight into the canonical SWIZZLE_128B K-major layout (8 lanes fetch
 //     one 128-byte row segment: fully coalesced) and completed on mbarriers with cp.async.mbarrier.arrive.noinc, so
 //     the issuing threads never wait for data (see producer_loop for the two alternatives that were measured);
-//   * accumulators live in TMEM (4 M-tiles x 64 columns per pair, double buffered = 512 columns), so the epilogue
-//     of pair p (TMEM -> cosine tile in smem -> model-specific pooling) overlaps the gather + MMAs of pair p+1.
+//   * accumulators live in TMEM: one buffer = 256 doc columns, two buffers, work unit = (pair, half of the doc tile), so
+//     the drain of unit u (TMEM -> cosine tile in smem) and the model-specific pooling overlap gather + MMA of u+1.
 //
-// Warp roles (416 threads): warps 0-7 epilogue (warp % 4 = the TMEM lane quarter it may read), warps 8-11 gather
-// producers, warp 12 = MMA issuer + TMEM allocator.
+// Warp roles (416 threads): warps 0-7 epilogue (warps 0/4 read the q_hi rows = TMEM lanes 0-31, warps 1/5 the q_lo rows
+// = lanes 32-63), warps 8-11 gather producers, warp 12 = MMA issuer + TMEM allocator.
 #pragma once
 #include "simtile.cuh"
 #include "tc_common.cuh"
@@ -29,13 +32,14 @@ namespace simtc {
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
 constexpr int EPI_THREADS = EPI_WARPS * 32, PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = EPI_THREADS + PROD_THREADS + 32;
-constexpr int ATOM_K = 64;                        // bf16 elements per 128-byte swizzle row
-constexpr int MAX_ATOMS = 5;                      // pitch <= 320
-constexpr int MT = 128;                           // docs per M tile
-constexpr int Q_ATOM_BYTES = 64 * 128;            // [q_hi;q_lo] 64 rows x 128 B
-constexpr int D_STAGE_BYTES = MT * 128;           // one plane (hi or lo) of 128 doc rows x one 64-element K atom = 16 KB
-constexpr int D_STAGES = 4;                       // ring depth
-constexpr int ACC_COLS_PER_MT = 64, ACC_COLS_PER_PAIR = 256;
+constexpr int ATOM_K = 64;                    // bf16 elements per 128-byte swizzle row
+constexpr int MAX_ATOMS = 5;                  // pitch <= 320
+constexpr int NT_DOCS = 256;                  // doc rows per MMA (N) = per work unit
+constexpr int Q_ATOM_BYTES = 64 * 128;        // [q_hi;q_lo] 64 rows x 128 B
+constexpr int D_STAGE_BYTES = NT_DOCS * 128;  // one plane (hi or lo) of 256 doc rows x one 64-element K atom = 32 KB
+constexpr int D_STAGES = 2;                   // ring depth
+constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
+constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
 
 struct Smem {
   unsigned char* q[2];        // [atoms][64 rows][128 B]
@@ -43,7 +47,8 @@ struct Smem {
   float* sim;                 // [SIM_ROWS][SIM_PITCH]
   int* qrow;                  // [QT]   table rows of the pair being gathered (producer)
   int* drow;                  // [DT]
-  int* qid;                   // [QT]      ids of the pair being drained (epilogue)
+  int* qid;                   // [QT]   ids of the pair being drained (epilogue)
+  int* did;                   // [DT]
   uint64_t *q_full, *q_empty, *d_full, *d_empty, *acc_full, *acc_empty;
   uint32_t* tmem_slot;
   float* extra;               // model-specific scratch
@@ -51,7 +56,7 @@ struct Smem {
 
 __host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes) {
   return 1024 + (size_t)2 * atoms * Q_ATOM_BYTES + (size_t)D_STAGES * D_STAGE_BYTES + (size_t)SIM_ROWS * SIM_PITCH * 4 +
-         (size_t)(QT + DT + QT) * 4 + 16 * 8 + 16 + extra_bytes;
+         (size_t)(2 * QT + 2 * DT) * 4 + 16 * 8 + 16 + extra_bytes;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
@@ -67,7 +72,8 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
   s.qrow = reinterpret_cast<int*>(p);
   s.drow = s.qrow + QT;
   s.qid = s.drow + DT;
-  p += (QT + DT + QT) * 4;
+  s.did = s.qid + QT;
+  p += (2 * QT + 2 * DT) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
   s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + D_STAGES, s.acc_full = b + 4 + 2 * D_STAGES,
   s.acc_empty = b + 6 + 2 * D_STAGES;
@@ -78,6 +84,8 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
+__device__ __forceinline__ void drain_barrier() { asm volatile("bar.sync 3, 128;" ::: "memory"); }  // epilogue warps 0,1,4,5
 
 struct Problem {
   const long long* q;
@@ -90,6 +98,8 @@ struct Problem {
   int debug;                // CAPR_DEBUG_* profiling switches (0 in production)
 };
 
+__device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
+
 // Common prologue: barriers + TMEM.  Call from all threads; returns the TMEM base.
 __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
   const int warp = tid >> 5;
@@ -98,7 +108,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
       tc::mbar_init(&s.q_full[i], PROD_THREADS);
       tc::mbar_init(&s.q_empty[i], 1);
       tc::mbar_init(&s.acc_full[i], 1);
-      tc::mbar_init(&s.acc_empty[i], EPI_WARPS);
+      tc::mbar_init(&s.acc_empty[i], 4);  // the four draining warps
     }
     for (int i = 0; i < D_STAGES; ++i) {
       tc::mbar_init(&s.d_full[i], PROD_THREADS);
@@ -124,22 +134,21 @@ __device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int 
 }
 
 // ---- producer warps: gather the query block and the doc stages of every pair of this CTA ----------------------------
-// 4 warps.  Work items, in order, per pair: the Q block, then for every (M tile, K atom): hi plane, lo plane.  Rows are
-// copied with 16-byte cp.async straight into the SWIZZLE_128B operand layout (8 lanes fetch one 128-byte row segment:
-// fully coalesced) and each thread posts cp.async.mbarrier.arrive.noinc on the stage's barrier, which fires when ITS
-// copies have landed -- the issuing thread never waits for data, so all D_STAGES stages are in flight.  (This is the
-// cp.async -> UMMA hand-off CUTLASS uses in sm100_mma_cpasync_warpspecialized.hpp.  Two alternatives were measured and
-// dropped: wait_group + fence.proxy.async + arrive serialises on the fence, 7.4 M pairs/s ceiling; TMA tile::gather4
-// of 128-byte rows costs ~80 cycles per instruction, 2.6 M pairs/s.)
+// 4 warps.  Work items, in order, per pair: the Q block, then for every (half, K atom): hi plane, lo plane of 256 doc
+// rows.  Rows are copied with 16-byte cp.async straight into the SWIZZLE_128B operand layout (8 lanes fetch one
+// 128-byte row segment: fully coalesced) and each thread posts cp.async.mbarrier.arrive.noinc on the stage's barrier,
+// which fires when ITS copies have landed -- the issuing thread never waits for data, so every stage is in flight.
+// (This is the cp.async -> UMMA hand-off CUTLASS uses in sm100_mma_cpasync_warpspecialized.hpp.  Two alternatives were
+// measured and dropped: wait_group + fence.proxy.async + arrive serialises on the fence, 7.4 M pairs/s ceiling; TMA
+// tile::gather4 of 128-byte rows costs ~80 cycles per instruction, 2.6 M pairs/s.)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
 __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, int ptid /*0..127*/) {
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int last_chunks = (pr.pitch - (atoms - 1) * ATOM_K) / 8;  // 16-byte chunks that exist in the last atom
-  const int n_mt = (pr.D + MT - 1) / MT;
+  const int halves = halves_of(pr);
   const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
   const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
   uint32_t q_phase[2] = {0, 0}, d_phase = 0;
@@ -166,19 +175,19 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
       }
     }
     cp_async_arrive_noinc(&s.q_full[b]);
-    for (int mt = 0; mt < n_mt; ++mt) {
-      size_t off[8];
+    for (int h = 0; h < halves; ++h) {
+      unsigned off[16];  // element offsets of this thread's 16 rows (V * pitch < 2^31 is checked on the host)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) off[j] = (size_t)s.drow[mt * MT + rsub + 16 * j] * pr.pitch + sub * 8;
+      for (int j = 0; j < 16; ++j) off[j] = (unsigned)s.drow[h * NT_DOCS + rsub + 16 * j] * (unsigned)pr.pitch + (unsigned)(sub * 8);
       for (int a = 0; a < atoms; ++a) {
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
           const uint32_t base = tc::smem_u32(s.d[d_stage]);
-          if ((a + 1 < atoms || sub < last_chunks) && !(pr.debug & 0x800)) {  // the tail chunks of a partial last atom are never read by the MMAs
+          if ((a + 1 < atoms || sub < last_chunks) && !(pr.debug & 0x800)) {  // tail chunks of a partial last atom are never read
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const int r = rsub + 16 * j;
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
             }
@@ -196,38 +205,37 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 // ---- MMA issuer: the WHOLE warp runs the loop (waits are warp-wide), one elected lane issues ----------------------------
 // Keeping the control flow warp-uniform lets ptxas hold descriptors / addresses in uniform registers; issuing from a
 // divergent `if (lane == 0)` region instead costs ~150 cycles per tcgen05.mma (R2UR chains + a serialising
-// ELECT/BRA.U.ANY loop around every UTCHMMA), which capped the first version of this kernel at 8.5 M pairs/s.
+// ELECT/BRA.U.ANY loop around every UTCHMMA).
 __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint32_t tmem_base) {
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
-  const int n_mt = (pr.D + MT - 1) / MT;
-  const uint32_t idesc64 = tc::make_instr_desc(tc::FMT_BF16, MT, 64);
-  const uint32_t idesc32 = tc::make_instr_desc(tc::FMT_BF16, MT, 32);
+  const int halves = halves_of(pr);
+  const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, 128, NT_DOCS);
   const bool skip = (pr.debug & 0x400) != 0;
   uint32_t q_phase[2] = {0, 0}, acc_phase[2] = {0, 0}, d_phase = 0;
-  int d_stage = 0, it = 0;
+  int d_stage = 0, it = 0, unit = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
-    tc::mbar_wait(&s.acc_empty[b], acc_phase[b] ^ 1);
-    acc_phase[b] ^= 1;
     tc::mbar_wait(&s.q_full[b], q_phase[b]);
     q_phase[b] ^= 1;
-    tc::tc_fence_after();
     const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.q[b]));
-    for (int mt = 0; mt < n_mt; ++mt) {
-      const uint32_t d_tmem = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT);
+    for (int h = 0; h < halves; ++h, ++unit) {
+      const int ab = unit & 1;
+      tc::mbar_wait(&s.acc_empty[ab], acc_phase[ab] ^ 1);
+      acc_phase[ab] ^= 1;
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
       for (int a = 0; a < atoms; ++a) {
-        const uint64_t bq = q_desc + (uint64_t)((a * Q_ATOM_BYTES) >> 4);
+        const uint64_t aq = q_desc + (uint64_t)((a * Q_ATOM_BYTES) >> 4);
         const int ksteps = skip ? 0 : min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           tc::mbar_wait(&s.d_full[d_stage], d_phase);
           tc::tc_fence_after();
-          const uint64_t ad = tc::make_sw128_kmajor_desc(tc::smem_u32(s.d[d_stage]));
+          const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.d[d_stage]));
           if (tc::elect_one()) {
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
-              if (plane == 0) tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc64, (a | k) != 0);  // [d_hi.q_hi | d_hi.q_lo]
-              else tc::umma_f16(d_tmem, ad + koff, bq + koff, idesc32, true);                      //  += d_lo.q_hi
+              tc::umma_f16(d_tmem, aq + koff, bd + koff, idesc, (a | plane | k) != 0);
             }
             tc::umma_commit(&s.d_empty[d_stage]);
           }
@@ -235,61 +243,77 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
           if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
         }
       }
+      if (tc::elect_one()) {
+        tc::umma_commit(&s.acc_full[ab]);
+        if (h + 1 == halves) tc::umma_commit(&s.q_empty[b]);
+      }
+      __syncwarp();
     }
-    if (tc::elect_one()) {
-      tc::umma_commit(&s.q_empty[b]);
-      tc::umma_commit(&s.acc_full[b]);
-    }
-    __syncwarp();
   }
 }
 
 // ---- epilogue helper: drain the accumulators of one pair into s.sim -------------------------------------------------
-// Called by the 256 epilogue threads.  After it returns (it ends with epi_barrier) s.sim holds the cosine tile.
-__device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uint32_t tmem_base, int pair, int b, uint32_t acc_parity,
-                                           int etid, bool skip_stores = false) {
-  const int warp = etid >> 5, lane = etid & 31, quarter = warp & 3, half = warp >> 2;
-  const int n_mt = (pr.D + MT - 1) / MT;
+// Called by the 256 epilogue threads with the index of the pair's first work unit.  Warps 0 and 4 hold the q_hi rows
+// (TMEM lanes 0-31, one query per lane), warps 1 and 5 the q_lo rows (lanes 32-63); warps 0/1 take doc columns 0-127 of
+// each half, warps 4/5 columns 128-255.  The lo warp parks its partial products in the tile, the hi warp adds its own,
+// applies the exact-match rules of simtile.cuh::store_sim_tile and writes the cosine back.  Row stride 516 floats makes
+// the one-row-per-lane 16-byte stores conflict-free.  Ends with epi_barrier: afterwards s.sim holds the whole tile and
+// s.qid / s.did the ids of the pair.
+__device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uint32_t tmem_base, int pair, int first_unit,
+                                           uint32_t (&acc_phase)[2], int etid, bool skip_stores = false) {
+  const int warp = etid >> 5, lane = etid & 31;
+  const int halves = halves_of(pr);
   if (etid < QT) s.qid[etid] = id_as_int(etid < pr.Q ? pr.q[(size_t)pair * pr.Q + etid] : 0);
+  for (int i = etid; i < DT; i += EPI_THREADS) s.did[i] = id_as_int(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0);
   epi_barrier();
-  tc::mbar_wait(&s.acc_full[b], acc_parity);
-  tc::tc_fence_after();
+  if ((warp & 2) == 0) {  // warps 0,1,4,5 drain
+    const bool is_lo = (warp & 1) != 0;
+    const int col_half = warp >> 2;  // 0: columns 0-127, 1: columns 128-255 of the unit
+    const uint32_t lane_off = (uint32_t)((warp & 1) * 32) << 16;
+    const int qi = s.qid[lane];
+    for (int h = 0; h < halves; ++h) {
+      const int ab = (first_unit + h) & 1;
+      tc::mbar_wait(&s.acc_full[ab], acc_phase[ab]);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col = col_half * 128 + cc * 32;  // column inside the unit
+        const int doc0 = h * NT_DOCS + col;
+        float v[32];
+        tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(ab * ACC_COLS + col), v);
+        tc::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(s.sim + lane * SIM_PITCH + doc0);
+        if (is_lo && !skip_stores) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int mt = half * 2 + h;
-    if (mt < n_mt && !skip_stores) {
-      const int doc = mt * MT + quarter * 32 + lane;
-      const int did = id_as_int(doc < pr.D ? pr.d[(size_t)pair * pr.D + doc] : 0);
-      const uint32_t taddr = tmem_base + (uint32_t)(b * ACC_COLS_PER_PAIR + mt * ACC_COLS_PER_MT) + ((uint32_t)(quarter * 32) << 16);
-      float hh[32], hl[32];
-      tc::tmem_ld_32x32(taddr, hh);
-      tc::tmem_ld_32x32(taddr + 32, hl);
-      tc::tmem_ld_wait();
-      // exact-match rules of simtile.cuh::store_sim_tile, branch-free: a doc token matches at most the few query
-      // positions that hold the same id, so test the cheap "any match" first (warp-uniform skip in the common case)
-      bool any = false;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) any |= (s.qid[i] == did);
-      any = any && did != 0;
-      if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = hh[i] + hl[i];
-          const int qi = s.qid[i];
-          const bool same = qi == did;
-          v = (same && qi < 0) ? v + 1.0f : v;
-          v = (same && qi > 0 && v > 0.5f) ? 1.0f : v;
-          s.sim[i * SIM_PITCH + doc] = v;
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-      } else {
+        drain_barrier();  // lo partials are in the tile
+        if (!is_lo && !skip_stores) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s.sim[i * SIM_PITCH + doc] = hh[i] + hl[i];
+          for (int j = 0; j < 8; ++j) {
+            const float4 l = dst[j];
+            v[4 * j] += l.x, v[4 * j + 1] += l.y, v[4 * j + 2] += l.z, v[4 * j + 3] += l.w;
+          }
+          if (qi != 0) {  // identical ids: OOV exact match (+1) or in-vocabulary snap to 1.0
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool same = s.did[doc0 + j] == qi;
+              v[j] = (same && qi < 0) ? v[j] + 1.0f : v[j];
+              v[j] = (same && qi > 0 && v[j] > 0.5f) ? 1.0f : v[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
       }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.acc_empty[ab]);
+      acc_phase[ab] ^= 1;
     }
+  } else {
+    for (int h = 0; h < halves; ++h) acc_phase[(first_unit + h) & 1] ^= 1;  // same phase bookkeeping in every warp
   }
-  tc::tc_fence_before();
-  __syncwarp();
-  if (lane == 0) tc::mbar_arrive(&s.acc_empty[b]);
   epi_barrier();
 }
 
