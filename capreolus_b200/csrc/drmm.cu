@@ -44,25 +44,26 @@ struct EpiSync {
   __device__ __forceinline__ void operator()() const { simtc::epi_barrier(); }
 };
 
-// Bin the `ncols` cosines of every query row of the tile (8 warps x 4 rows).  `dids` = the doc ids of these columns.
-template <int SLOTS>
+// Bin the `ncols` cosines of every query row of the tile (8 warps x 4 rows; row stride PITCH floats, at most COLS
+// columns).  `did_smem` = the doc ids of these columns.
+template <int SLOTS, int PITCH, int COLS>
 __device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid, const int* did_smem, int ncols, const DrmmArgs& a,
                                                 const float* ub, int* cnt, int warp, int lane) {
   const float guess_scale = 0.5f * (float)a.nbins;
   // this lane's doc ids (columns lane, lane+32, ...), fetched once for the 4 query rows of the warp
-  int dd[DT / 32];
+  int dd[COLS / 32];
 #pragma unroll
-  for (int t = 0; t < DT / 32; ++t) {
+  for (int t = 0; t < COLS / 32; ++t) {
     const int c = lane + 32 * t;
     dd[t] = c < ncols ? did_smem[c] : 0;
   }
   for (int r = 0; r < 4; ++r) {
     const int qrow = warp * 4 + r;
-    const float* row = sim + qrow * SIM_PITCH;
+    const float* row = sim + qrow * PITCH;
     int* c_row = cnt + qrow * SLOTS;
     const int qi = qid[qrow];
 #pragma unroll
-    for (int t = 0; t < DT / 32; ++t) {
+    for (int t = 0; t < COLS / 32; ++t) {
       if (t * 32 >= ncols) break;  // warp-uniform
       const int c = lane + 32 * t;
       const int did = dd[t];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
     const long long* dids = a.d + (size_t)pair * a.D;
     for (int d0 = 0; d0 < a.D; d0 += DT) {
       build_sim_tile(s, a.table, a.pitch, a.V, qids, a.Q, dids, d0, a.D, d0 == 0, tid);  // also orders the cnt reset
-      drmm_count_tile<MAX_SLOTS>(s.sim, s.qid, s.did, min(DT, a.D - d0), a, ub, cnt, warp, lane);
+      drmm_count_tile<MAX_SLOTS, SIM_PITCH, DT>(s.sim, s.qid, s.did, min(DT, a.D - d0), a, ub, cnt, warp, lane);
       __syncthreads();
     }
     drmm_finish<MAX_SLOTS>(a, pair, cnt, z, warp, lane, BlockSync());
@@ -171,31 +172,44 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
   }
 }
 
-// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh); same counting + finish code on the 8 epilogue warps.
-__global__ void __launch_bounds__(simtc::THREADS, 1) drmm_tc_kernel(const DrmmArgs a) {
+// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh, pipelined epilogue); same counting + finish code on the 8
+// pooling warps, one half tile (256 docs) at a time.
+__global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const DrmmArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
-  int* cnt = reinterpret_cast<int*>(s.extra);                     // [QT][MAX_SLOTS_TC]
+  static_assert((QT * MAX_SLOTS_TC + MAX_SLOTS_TC + QT) <= SPARE_FLOATS, "DRMM scratch must fit behind the two half tiles");
+  int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][MAX_SLOTS_TC]
   float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS_TC);  // [MAX_SLOTS_TC]
   float* z = ub + MAX_SLOTS_TC;                                   // [QT]
-  if (tid < a.nbins) ub[tid] = a.bin_ub[tid];
-  const uint32_t tmem_base = setup(s, tid);
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE);
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     mma_loop(s, a.pr, tmem_base);
+  } else if (is_drain_warp(warp)) {
+    drain_loop(s, a.pr, tmem_base, warp, lane);
   } else {
-    uint32_t acc_phase[2] = {0, 0};
-    int unit = 0;
-    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
-      for (int i = tid; i < QT * MAX_SLOTS_TC; i += EPI_THREADS) cnt[i] = 0;  // ordered by drain_pair's barriers
-      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);
-      drmm_count_tile<MAX_SLOTS_TC>(s.sim, s.qid, s.did, a.D, a, ub, cnt, warp, lane);
+    const int pw = pool_index(warp), ptid = pw * 32 + lane;
+    const int halves = halves_of(a.pr);
+    if (ptid < a.nbins) ub[ptid] = a.bin_ub[ptid];
+    PoolSync ps;
+    int unit = 0, it = 0;
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
+      for (int i = ptid; i < QT * MAX_SLOTS_TC; i += POOL_WARPS * 32) cnt[i] = 0;
+      epi_barrier();  // the 8 pooling warps: counters (and, first time, the bounds) are in place
+      const int* qid = s.qid + (it & 1) * QT;
+      for (int h = 0; h < halves; ++h, ++unit) {
+        const int ub_i = unit & 1;
+        ps.wait_full(s, ub_i);
+        drmm_count_tile<MAX_SLOTS_TC, HALF_PITCH, NT_DOCS>(half_tile(s, ub_i), qid, s.did + (it & 1) * DT + h * NT_DOCS,
+                                                           min(NT_DOCS, a.D - h * NT_DOCS), a, ub, cnt, pw, lane);
+        ps.release(s, ub_i, lane);
+      }
       epi_barrier();
-      drmm_finish<MAX_SLOTS_TC>(a, pair, cnt, z, warp, lane, EpiSync());
-      epi_barrier();
+      drmm_finish<MAX_SLOTS_TC>(a, pair, cnt, z, pw, lane, EpiSync());
+      epi_barrier();  // z / cnt are rewritten by the next pair
     }
   }
   teardown(s, tmem_base, tid);
@@ -257,11 +271,11 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
              nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
              simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}};
-  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)QT * MAX_SLOTS_TC * sizeof(int) + (MAX_SLOTS_TC + QT) * sizeof(float));
+  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, 0);
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
-  drmm_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, (cudaStream_t)stream>>>(a);
+  drmm_tc_kernel<<<B < sms ? B : sms, simtc::THREADS_PIPE, smem, (cudaStream_t)stream>>>(a);
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }

@@ -6,8 +6,8 @@
 //
 // Same math and same quirks as knrm.cu (sum over ALL doc positions, live-row test on the cosine row-sum, log(S+1e-6),
 // combine); only the producer of the cosine tile differs: gather -> UMMA -> TMEM instead of gather -> FFMA.  The
-// pooling epilogue (MUFU ex2 bound, 180 k exponentials per pair) runs on 8 warps while the producer and MMA warps are
-// already working on the next pair.
+// epilogue is a pipeline of its own (simtc.cuh): 4 warps drain TMEM into half tiles of 32 x 256 cosines, 8 warps pool
+// them (MUFU ex2 bound, 180 k exponentials per pair), while the producer and MMA warps work on the next pair.
 #include "simtc.cuh"
 
 namespace capr {
@@ -23,20 +23,23 @@ struct KnrmTcArgs {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTcArgs a) {
+__global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const KnrmTcArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
-  float* sPart = s.extra;  // [EPI_WARPS][KT] per-warp partial features
-  const uint32_t tmem_base = setup(s, tid);
+  float* sPart = s.extra;  // [2][POOL_WARPS][KT] per-warp partial features, double-buffered by pair parity
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE);
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     mma_loop(s, a.pr, tmem_base);
+  } else if (is_drain_warp(warp)) {
+    drain_loop(s, a.pr, tmem_base, warp, lane);
   } else {
-    // ===================== epilogue: 8 warps, 4 query rows each =====================
+    // ===================== pooling: 8 warps, 4 query rows each, one half tile (256 docs) at a time =====================
+    const int pw = pool_index(warp);
     float mu[KT], cc[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
@@ -44,46 +47,61 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
       mu[k] = k < a.K ? a.mu[k] : 0.f;
       cc[k] = -0.5f * 1.4426950408889634f / (sg * sg);
     }
-    constexpr int ROWS_PER_WARP = QT / EPI_WARPS;  // 4
-    uint32_t acc_phase[2] = {0, 0};
-    int unit = 0;
-    for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, unit += halves_of(a.pr)) {
-      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid, (a.flags & CAPR_DEBUG_SKIP_DRAIN) != 0);
-      // lane k accumulates this warp's share of R_k = sum over its live rows of log(S_k + 1e-6)   (KNRM.py:50-53)
-      float R_part = 0.f;
-      if (!(a.flags & CAPR_DEBUG_SKIP_POOL)) {
+    constexpr int ROWS_PER_WARP = QT / POOL_WARPS;  // 4
+    const int halves = halves_of(a.pr);
+    PoolSync ps;
+    int unit = 0, it = 0;
+    for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, ++it) {
+      float S[ROWS_PER_WARP][KT], rs[ROWS_PER_WARP];
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_WARP; ++r) {
-          const float* row = s.sim + (warp * ROWS_PER_WARP + r) * SIM_PITCH;
-          float S[KT], rs = 0.f;
+      for (int r = 0; r < ROWS_PER_WARP; ++r) {
+        rs[r] = 0.f;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) S[k] = 0.f;
-          for (int c = lane; c < a.pr.D; c += 32) {
-            const float v = row[c];
-            rs += v;
+        for (int k = 0; k < KT; ++k) S[r][k] = 0.f;
+      }
+      for (int h = 0; h < halves; ++h, ++unit) {
+        const int ub = unit & 1;
+        ps.wait_full(s, ub);
+        const int ncols = min(NT_DOCS, a.pr.D - h * NT_DOCS);
+        if (!(a.flags & CAPR_DEBUG_SKIP_POOL)) {
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              const float adj = v - mu[k];
-              S[k] += ex2_approx(cc[k] * adj * adj);
+          for (int r = 0; r < ROWS_PER_WARP; ++r) {
+            const float* row = half_tile(s, ub) + (pw * ROWS_PER_WARP + r) * HALF_PITCH;
+#pragma unroll 2
+            for (int c = lane; c < ncols; c += 32) {
+              const float v = row[c];
+              rs[r] += v;
+#pragma unroll
+              for (int k = 0; k < KT; ++k) {
+                const float adj = v - mu[k];
+                S[r][k] += ex2_approx(cc[k] * adj * adj);
+              }
             }
           }
-          rs = warp_sum(rs);
-          float mine = 0.f;
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const float t = warp_sum(S[k]);
-            mine = lane == k ? t : mine;
-          }
-          if (rs != 0.0f && warp * ROWS_PER_WARP + r < a.pr.Q) R_part += logf(mine + 1e-6f);  // KNRM.py:51-52
         }
+        ps.release(s, ub, lane);
       }
-      if (lane < KT) sPart[warp * KT + lane] = R_part;
-      epi_barrier();
-      if (warp == 0) {
+      // lane k accumulates this warp's share of R_k = sum over its live rows of log(S_k + 1e-6)   (KNRM.py:50-53)
+      float R_part = 0.f;
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_WARP; ++r) {
+        const float rsum = warp_sum(rs[r]);
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const float t = warp_sum(S[r][k]);
+          mine = lane == k ? t : mine;
+        }
+        if (rsum != 0.0f && pw * ROWS_PER_WARP + r < a.pr.Q) R_part += logf(mine + 1e-6f);  // KNRM.py:51-52
+      }
+      float* part = sPart + (it & 1) * POOL_WARPS * KT;
+      if (lane < KT) part[pw * KT + lane] = R_part;
+      epi_barrier();  // the 8 pooling warps.  part[] of this parity is rewritten two pairs (= two barriers) later
+      if (pw == 0) {
         float R = 0.f;
         if (lane < a.K) {
 #pragma unroll
-          for (int w = 0; w < EPI_WARPS; ++w) R += sPart[w * KT + lane];  // fixed order over the 8 row groups
+          for (int w = 0; w < POOL_WARPS; ++w) R += part[w * KT + lane];  // fixed order over the 8 row groups
           if (a.feats) a.feats[(size_t)pair * a.K + lane] = R;
         }
         if (a.scores) {
@@ -102,7 +120,6 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) knrm_tc_kernel(const KnrmTc
           if (lane == 0) a.scores[pair] = out;
         }
       }
-      // the next drain_pair starts with an epi_barrier, which orders these reads before the next writes of s.sim / sS
     }
   }
   teardown(s, tmem_base, tid);
@@ -170,17 +187,17 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, flags & 0xF00};
   a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2, a.scores = scores, a.feats = feats;
   const int KT = K <= 11 ? 11 : 16;
-  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)(simtc::EPI_WARPS * KT) * sizeof(float));
+  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)(2 * simtc::POOL_WARPS * KT) * sizeof(float));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;
   cudaStream_t st = (cudaStream_t)stream;
   if (KT == 11) {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<11><<<grid, simtc::THREADS, smem, st>>>(a);
+    knrm_tc_kernel<11><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   } else {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<16><<<grid, simtc::THREADS, smem, st>>>(a);
+    knrm_tc_kernel<16><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   } else if (warp == EPI_WARPS + PROD_WARPS) {
     mma_loop(s, a.pr, tmem_base);
   } else {
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase = 0;
     int unit = 0;
     for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
       drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);

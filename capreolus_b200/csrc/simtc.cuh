@@ -20,8 +20,12 @@
 //   * accumulators live in TMEM: one buffer = 256 doc columns, two buffers, work unit = (pair, half of the doc tile), so
 //     the drain of unit u (TMEM -> cosine tile in smem) and the model-specific pooling overlap gather + MMA of u+1.
 //
-// Warp roles (416 threads): warps 0-7 epilogue (warps 0/4 read the q_hi rows = TMEM lanes 0-31, warps 1/5 the q_lo rows
-// = lanes 32-63), warps 8-11 gather producers, warp 12 = MMA issuer + TMEM allocator.
+// Warp roles: warps 0-7 epilogue (warps 0/4 read the q_hi rows = TMEM lanes 0-31, warps 1/5 the q_lo rows = lanes
+// 32-63), warps 8-11 gather producers, warp 12 = MMA issuer + TMEM allocator (416 threads: PACRR, whose conv epilogue
+// needs the whole tile with its halo and runs drain -> conv sequentially on warps 0-7).
+// KNRM and DRMM pool column-additively, so they use the PIPELINED epilogue (544 threads): warps 0,1,4,5 only drain, into
+// two half-tile buffers of 32 x 256 cosines, and 8 pooling warps (2,3,6,7 + 13-16) consume them -- drain of half h+1
+// overlaps pooling of half h, across pair boundaries.
 #pragma once
 #include "simtile.cuh"
 #include "tc_common.cuh"
@@ -40,43 +44,52 @@ constexpr int D_STAGE_BYTES = NT_DOCS * 128;  // one plane (hi or lo) of 256 doc
 constexpr int D_STAGES = 2;                   // ring depth
 constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
 constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
+constexpr int POOL_WARPS = 8;                 // pipelined epilogue: pooling warps
+constexpr int THREADS_PIPE = THREADS + 4 * 32;  // + warps 13-16
+constexpr int HALF_PITCH = NT_DOCS + 4;       // 260 floats: one-row-per-lane float4 stores are conflict-free (260 % 32 == 4)
+constexpr int HALF_FLOATS = QT * HALF_PITCH;  // one half tile = 33 280 B; two of them fit in the full-tile region
+constexpr int SPARE_FLOATS = SIM_ROWS * SIM_PITCH - 2 * HALF_FLOATS;  // 1 936 floats left over there (DRMM counters)
 
 struct Smem {
-  unsigned char* q[2];        // [atoms][64 rows][128 B]
-  unsigned char* d[D_STAGES];
+  unsigned char* q0;          // 2 x [atoms][64 rows][128 B]
+  int q_stride;
+  unsigned char* d0;          // D_STAGES x 32 KB
+  __device__ __forceinline__ unsigned char* qbuf(int b) const { return q0 + b * q_stride; }
+  __device__ __forceinline__ unsigned char* dbuf(int i) const { return d0 + i * D_STAGE_BYTES; }
   float* sim;                 // [SIM_ROWS][SIM_PITCH]
   int* qrow;                  // [QT]   table rows of the pair being gathered (producer)
   int* drow;                  // [DT]
-  int* qid;                   // [QT]   ids of the pair being drained (epilogue)
-  int* did;                   // [DT]
-  uint64_t *q_full, *q_empty, *d_full, *d_empty, *acc_full, *acc_empty;
+  int* qid;                   // [2][QT]   ids of the pair being drained / pooled (epilogue; pipelined mode: by pair parity)
+  int* did;                   // [2][DT]
+  uint64_t *q_full, *q_empty, *d_full, *d_empty, *acc_full, *acc_empty, *half_full, *half_empty;
   uint32_t* tmem_slot;
   float* extra;               // model-specific scratch
 };
 
 __host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes) {
   return 1024 + (size_t)2 * atoms * Q_ATOM_BYTES + (size_t)D_STAGES * D_STAGE_BYTES + (size_t)SIM_ROWS * SIM_PITCH * 4 +
-         (size_t)(2 * QT + 2 * DT) * 4 + 16 * 8 + 16 + extra_bytes;
+         (size_t)(3 * QT + 3 * DT) * 4 + 16 * 8 + 16 + extra_bytes;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
   Smem s;
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  s.q[0] = p;
-  s.q[1] = p + atoms * Q_ATOM_BYTES;
+  s.q0 = p;
+  s.q_stride = atoms * Q_ATOM_BYTES;
   p += 2 * atoms * Q_ATOM_BYTES;
-  for (int i = 0; i < D_STAGES; ++i) s.d[i] = p + i * D_STAGE_BYTES;
+  s.d0 = p;
   p += D_STAGES * D_STAGE_BYTES;
   s.sim = reinterpret_cast<float*>(p);
   p += SIM_ROWS * SIM_PITCH * 4;
   s.qrow = reinterpret_cast<int*>(p);
   s.drow = s.qrow + QT;
   s.qid = s.drow + DT;
-  s.did = s.qid + QT;
-  p += (2 * QT + 2 * DT) * 4;
+  s.did = s.qid + 2 * QT;
+  p += (3 * QT + 3 * DT) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
   s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + D_STAGES, s.acc_full = b + 4 + 2 * D_STAGES,
   s.acc_empty = b + 6 + 2 * D_STAGES;
+  s.half_full = b + 8 + 2 * D_STAGES, s.half_empty = b + 10 + 2 * D_STAGES;  // D_STAGES == 2: 16 barriers in all
   p += 16 * 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   s.extra = reinterpret_cast<float*>(p + 16);
@@ -101,7 +114,7 @@ struct Problem {
 __device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
 
 // Common prologue: barriers + TMEM.  Call from all threads; returns the TMEM base.
-__device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
+__device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads = THREADS) {
   const int warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -109,6 +122,8 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
       tc::mbar_init(&s.q_empty[i], 1);
       tc::mbar_init(&s.acc_full[i], 1);
       tc::mbar_init(&s.acc_empty[i], 4);  // the four draining warps
+      tc::mbar_init(&s.half_full[i], 2);  // the two q_hi draining warps
+      tc::mbar_init(&s.half_empty[i], POOL_WARPS);
     }
     for (int i = 0; i < D_STAGES; ++i) {
       tc::mbar_init(&s.d_full[i], PROD_THREADS);
@@ -116,7 +131,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid) {
     }
     tc::fence_barrier_init();
   }
-  for (int i = tid; i < SIM_ROWS * SIM_PITCH; i += THREADS) s.sim[i] = 0.f;
+  for (int i = tid; i < SIM_ROWS * SIM_PITCH; i += nthreads) s.sim[i] = 0.f;
   if (warp == EPI_WARPS + PROD_WARPS) tc::tmem_alloc(s.tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
@@ -151,7 +166,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   const int halves = halves_of(pr);
   const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
   const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
-  uint32_t q_phase[2] = {0, 0}, d_phase = 0;
+  uint32_t q_phase = 0, d_phase = 0;  // q_phase: one bit per buffer
   int d_stage = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
@@ -160,10 +175,10 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
     prod_barrier();
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
-    tc::mbar_wait(&s.q_empty[b], q_phase[b] ^ 1);
-    q_phase[b] ^= 1;
+    tc::mbar_wait(&s.q_empty[b], ((q_phase >> b) & 1) ^ 1);
+    q_phase ^= 1u << b;
     {
-      const uint32_t qbase = tc::smem_u32(s.q[b]);
+      const uint32_t qbase = tc::smem_u32(s.qbuf(b));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = rsub + 16 * j;  // 0..63
@@ -184,7 +199,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
         for (int plane = 0; plane < 2; ++plane) {
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
-          const uint32_t base = tc::smem_u32(s.d[d_stage]);
+          const uint32_t base = tc::smem_u32(s.dbuf(d_stage));
           if ((a + 1 < atoms || sub < last_chunks) && !(pr.debug & 0x800)) {  // tail chunks of a partial last atom are never read
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -211,17 +226,17 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   const int halves = halves_of(pr);
   const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, 128, NT_DOCS);
   const bool skip = (pr.debug & 0x400) != 0;
-  uint32_t q_phase[2] = {0, 0}, acc_phase[2] = {0, 0}, d_phase = 0;
+  uint32_t q_phase = 0, acc_phase = 0, d_phase = 0;  // q/acc: one bit per buffer
   int d_stage = 0, it = 0, unit = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = it & 1;
-    tc::mbar_wait(&s.q_full[b], q_phase[b]);
-    q_phase[b] ^= 1;
-    const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.q[b]));
+    tc::mbar_wait(&s.q_full[b], (q_phase >> b) & 1);
+    q_phase ^= 1u << b;
+    const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.qbuf(b)));
     for (int h = 0; h < halves; ++h, ++unit) {
       const int ab = unit & 1;
-      tc::mbar_wait(&s.acc_empty[ab], acc_phase[ab] ^ 1);
-      acc_phase[ab] ^= 1;
+      tc::mbar_wait(&s.acc_empty[ab], ((acc_phase >> ab) & 1) ^ 1);
+      acc_phase ^= 1u << ab;
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
       for (int a = 0; a < atoms; ++a) {
@@ -231,7 +246,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
         for (int plane = 0; plane < 2; ++plane) {
           tc::mbar_wait(&s.d_full[d_stage], d_phase);
           tc::tc_fence_after();
-          const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.d[d_stage]));
+          const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.dbuf(d_stage)));
           if (tc::elect_one()) {
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
@@ -260,7 +275,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
 // the one-row-per-lane 16-byte stores conflict-free.  Ends with epi_barrier: afterwards s.sim holds the whole tile and
 // s.qid / s.did the ids of the pair.
 __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uint32_t tmem_base, int pair, int first_unit,
-                                           uint32_t (&acc_phase)[2], int etid, bool skip_stores = false) {
+                                           uint32_t& acc_phase /* one bit per buffer */, int etid, bool skip_stores = false) {
   const int warp = etid >> 5, lane = etid & 31;
   const int halves = halves_of(pr);
   if (etid < QT) s.qid[etid] = id_as_int(etid < pr.Q ? pr.q[(size_t)pair * pr.Q + etid] : 0);
@@ -273,7 +288,7 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
     const int qi = s.qid[lane];
     for (int h = 0; h < halves; ++h) {
       const int ab = (first_unit + h) & 1;
-      tc::mbar_wait(&s.acc_full[ab], acc_phase[ab]);
+      tc::mbar_wait(&s.acc_full[ab], (acc_phase >> ab) & 1);
       tc::tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -309,13 +324,107 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s.acc_empty[ab]);
-      acc_phase[ab] ^= 1;
+      acc_phase ^= 1u << ab;
     }
   } else {
-    for (int h = 0; h < halves; ++h) acc_phase[(first_unit + h) & 1] ^= 1;  // same phase bookkeeping in every warp
+    for (int h = 0; h < halves; ++h) acc_phase ^= 1u << ((first_unit + h) & 1);  // same phase bookkeeping in every warp
   }
   epi_barrier();
 }
+
+// ---- pipelined epilogue (KNRM, DRMM) -----------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_drain_warp(int warp) { return warp < 8 && (warp & 2) == 0; }
+__device__ __forceinline__ bool is_pool_warp(int warp) { return (warp < 8 && (warp & 2) != 0) || warp > EPI_WARPS + PROD_WARPS; }
+__device__ __forceinline__ int pool_index(int warp) { return warp < 8 ? ((warp >> 2) * 2 + (warp & 1)) : 4 + (warp - (EPI_WARPS + PROD_WARPS + 1)); }
+__device__ __forceinline__ float* half_tile(const Smem& s, int hb) { return s.sim + hb * HALF_FLOATS; }
+__device__ __forceinline__ float* spare_scratch(const Smem& s) { return s.sim + 2 * HALF_FLOATS; }
+
+// Drain warps (0,1,4,5): all pairs of this CTA.  Half-tile buffer and TMEM buffer of a unit share the unit's parity.
+__device__ __forceinline__ void drain_loop(const Smem& s, const Problem& pr, uint32_t tmem_base, int warp, int lane) {
+  const int halves = halves_of(pr);
+  const bool is_lo = (warp & 1) != 0;
+  const int col_half = warp >> 2;
+  const int dtid = (warp >> 2) * 64 + (warp & 1) * 32 + lane;  // 0..127 over the four drain warps
+  const uint32_t lane_off = (uint32_t)((warp & 1) * 32) << 16;
+  const bool skip_stores = (pr.debug & CAPR_DEBUG_SKIP_DRAIN) != 0;
+  uint32_t full_phase = 0, empty_phase = 0;  // one bit per buffer
+  int unit = 0, it = 0;
+  for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
+    const int pp = it & 1;
+    int* qid = s.qid + pp * QT;
+    int* did = s.did + pp * DT;
+    int qi = 0;
+    for (int h = 0; h < halves; ++h, ++unit) {
+      const int ub = unit & 1;
+      tc::mbar_wait(&s.half_empty[ub], ((empty_phase >> ub) & 1) ^ 1);  // pooling is done with this half-tile buffer
+      empty_phase ^= 1u << ub;
+      if (h == 0) {
+        // ids of this pair.  Buffer pp was last read by the pooling of pair it-2, and that pooling released every one of
+        // its half tiles before the wait above could complete (buffer ub was last used by unit-2, which belongs to pair
+        // it-1 when halves == 2 and to pair it-2 when halves == 1).  The writes are ordered before half_full by the
+        // barrier below + the hi warps' arrive.
+        if (dtid < QT) qid[dtid] = id_as_int(dtid < pr.Q ? pr.q[(size_t)pair * pr.Q + dtid] : 0);
+        for (int i = dtid; i < DT; i += 128) did[i] = id_as_int(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0);
+        drain_barrier();
+        qi = qid[lane];
+      }
+      tc::mbar_wait(&s.acc_full[ub], (full_phase >> ub) & 1);
+      full_phase ^= 1u << ub;
+      tc::tc_fence_after();
+      float* tile = half_tile(s, ub);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col = col_half * 128 + cc * 32;
+        float v[32];
+        tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(ub * ACC_COLS + col), v);
+        tc::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(tile + lane * HALF_PITCH + col);
+        if (is_lo && !skip_stores) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        drain_barrier();  // lo partials are in the tile
+        if (!is_lo && !skip_stores) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 l = dst[j];
+            v[4 * j] += l.x, v[4 * j + 1] += l.y, v[4 * j + 2] += l.z, v[4 * j + 3] += l.w;
+          }
+          if (qi != 0) {  // identical ids: OOV exact match (+1) or in-vocabulary snap to 1.0 (simtile.cuh rules)
+            const int* dd = did + h * NT_DOCS + col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool same = dd[j] == qi;
+              v[j] = (same && qi < 0) ? v[j] + 1.0f : v[j];
+              v[j] = (same && qi > 0 && v[j] > 0.5f) ? 1.0f : v[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(&s.acc_empty[ub]);
+        if (!is_lo) tc::mbar_arrive(&s.half_full[ub]);
+      }
+    }
+  }
+}
+
+// Pooling-side handshake: wait for half `ub` of the current unit / hand the buffer back.
+struct PoolSync {
+  uint32_t phase = 0;  // one bit per buffer
+  __device__ __forceinline__ void wait_full(const Smem& s, int ub) {
+    tc::mbar_wait(&s.half_full[ub], (phase >> ub) & 1);
+    phase ^= 1u << ub;
+  }
+  __device__ __forceinline__ void release(const Smem& s, int ub, int lane) {
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&s.half_empty[ub]);
+  }
+};
 
 }  // namespace simtc
 }  // namespace capr

@@ -6,5 +6,5 @@ if [ "$rc" == "124" ]; then echo "HANG"; exit 1; fi
 b() { python bench.py --model $1 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1 $2', round(d['value']), 'pairs/s  frac', round(d['roofline']['frac'],3), ' e2e', round(d['e2e']['value']))"; }
 b knrm tc; b drmm tc; b pacrr tc
 CAPR_DEBUG_FLAGS=0x300 b knrm skip_pool_drain
-CAPR_DEBUG_FLAGS=0xB00 b knrm skip_pool_drain_gather
-CAPR_DEBUG_FLAGS=0x700 b knrm skip_pool_drain_mma
+CAPR_DEBUG_FLAGS=0x100 b knrm skip_pool
+CAPR_DEBUG_FLAGS=0x200 b knrm skip_drain_stores
