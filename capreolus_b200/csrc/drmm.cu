@@ -183,10 +183,10 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
   int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][MAX_SLOTS_TC]
   float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS_TC);  // [MAX_SLOTS_TC]
   float* z = ub + MAX_SLOTS_TC;                                   // [QT]
-  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE);
-  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    producer_loop(s, a.pr, tid - EPI_THREADS);
-  } else if (warp == EPI_WARPS + PROD_WARPS) {
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
+  if (is_producer_warp(warp)) {
+    producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
+  } else if (warp == MMA_WARP_PIPE) {
     mma_loop(s, a.pr, tmem_base);
   } else if (is_drain_warp(warp)) {
     drain_loop(s, a.pr, tmem_base, warp, lane);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
       epi_barrier();  // z / cnt are rewritten by the next pair
     }
   }
-  teardown(s, tmem_base, tid);
+  teardown(s, tmem_base, tid, MMA_WARP_PIPE);
 }
 
 }  // namespace capr

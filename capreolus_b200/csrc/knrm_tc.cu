@@ -29,16 +29,20 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
   float* sPart = s.extra;  // [2][POOL_WARPS][KT] per-warp partial features, double-buffered by pair parity
-  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE);
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
 
-  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    producer_loop(s, a.pr, tid - EPI_THREADS);
-  } else if (warp == EPI_WARPS + PROD_WARPS) {
+  if (is_producer_warp(warp)) {
+    producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
+  } else if (warp == MMA_WARP_PIPE) {
     mma_loop(s, a.pr, tmem_base);
   } else if (is_drain_warp(warp)) {
     drain_loop(s, a.pr, tmem_base, warp, lane);
   } else {
-    // ===================== pooling: 8 warps, 4 query rows each, one half tile (256 docs) at a time =====================
+    // ===================== pooling: 8 warps; lane = query row, warp = a 32-column slice of every half tile ============
+    // Each thread keeps the K running sums of ITS row over ITS columns (K + 1 accumulators, no shuffles in the loop; the
+    // one-row-per-lane float4 reads are conflict-free like the drain's stores).  At the end of the pair the 8 column
+    // slices are combined through shared memory: every warp parks its [32 rows][K+1] partials in its own slice of the
+    // last half tile (only this warp ever read those columns), then warp w reduces rows 4w..4w+3 in a fixed order.
     const int pw = pool_index(warp);
     float mu[KT], cc[KT];
 #pragma unroll
@@ -47,56 +51,76 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
       mu[k] = k < a.K ? a.mu[k] : 0.f;
       cc[k] = -0.5f * 1.4426950408889634f / (sg * sg);
     }
-    constexpr int ROWS_PER_WARP = QT / POOL_WARPS;  // 4
+    constexpr int ROWS_PER_WARP = QT / POOL_WARPS;  // 4 (second stage)
+    constexpr int SLICE = NT_DOCS / POOL_WARPS;     // 32 columns per warp and half
+    static_assert(KT + 1 <= SLICE, "partials of one row must fit in the warp's slice");
     const int halves = halves_of(a.pr);
     PoolSync ps;
     int unit = 0, it = 0;
     for (int pair = blockIdx.x; pair < a.pr.B; pair += gridDim.x, ++it) {
-      float S[ROWS_PER_WARP][KT], rs[ROWS_PER_WARP];
+      float S[KT], rs = 0.f;
 #pragma unroll
-      for (int r = 0; r < ROWS_PER_WARP; ++r) {
-        rs[r] = 0.f;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) S[r][k] = 0.f;
-      }
+      for (int k = 0; k < KT; ++k) S[k] = 0.f;
+      int ub = 0;
       for (int h = 0; h < halves; ++h, ++unit) {
-        const int ub = unit & 1;
+        ub = unit & 1;
         ps.wait_full(s, ub);
-        const int ncols = min(NT_DOCS, a.pr.D - h * NT_DOCS);
-        if (!(a.flags & CAPR_DEBUG_SKIP_POOL)) {
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_WARP; ++r) {
-            const float* row = half_tile(s, ub) + (pw * ROWS_PER_WARP + r) * HALF_PITCH;
+        const int nvalid = min(NT_DOCS, a.pr.D - h * NT_DOCS) - pw * SLICE;  // columns of this slice that exist
+        if (!(a.flags & CAPR_DEBUG_SKIP_POOL) && nvalid > 0) {
+          const float4* row = reinterpret_cast<const float4*>(half_tile(s, ub) + lane * HALF_PITCH + pw * SLICE);
 #pragma unroll 2
-            for (int c = lane; c < ncols; c += 32) {
-              const float v = row[c];
-              rs[r] += v;
+          for (int g = 0; g < SLICE / 4; ++g) {
+            const float4 x = row[g];
+            float v[4] = {x.x, x.y, x.z, x.w};
+            if (nvalid < SLICE) {  // warp-uniform: ragged tail of the doc tile
 #pragma unroll
-              for (int k = 0; k < KT; ++k) {
-                const float adj = v - mu[k];
-                S[r][k] += ex2_approx(cc[k] * adj * adj);
+              for (int j = 0; j < 4; ++j) {
+                const bool valid = g * 4 + j < nvalid;
+                rs += valid ? v[j] : 0.f;
+                v[j] = valid ? v[j] : 1e18f;  // every kernel underflows to exactly 0
               }
+            } else {
+              rs += (v[0] + v[1]) + (v[2] + v[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              float e[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float adj = v[j] - mu[k];
+                e[j] = ex2_approx(cc[k] * adj * adj);
+              }
+              S[k] += (e[0] + e[1]) + (e[2] + e[3]);
             }
           }
         }
-        ps.release(s, ub, lane);
+        if (h + 1 < halves) ps.release(s, ub, lane);  // the last half tile is kept for the cross-warp reduction
       }
+      float* tile = half_tile(s, ub);
+      {
+        float* mine = tile + lane * HALF_PITCH + pw * SLICE;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) mine[k] = S[k];
+        mine[KT] = rs;
+      }
+      epi_barrier();  // the 8 pooling warps
       // lane k accumulates this warp's share of R_k = sum over its live rows of log(S_k + 1e-6)   (KNRM.py:50-53)
       float R_part = 0.f;
 #pragma unroll
       for (int r = 0; r < ROWS_PER_WARP; ++r) {
-        const float rsum = warp_sum(rs[r]);
-        float mine = 0.f;
+        const int qrow = pw * ROWS_PER_WARP + r;
+        float t = 0.f;
+        if (lane <= KT) {
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const float t = warp_sum(S[r][k]);
-          mine = lane == k ? t : mine;
+          for (int w = 0; w < POOL_WARPS; ++w) t += tile[qrow * HALF_PITCH + w * SLICE + lane];  // fixed order over the slices
         }
-        if (rsum != 0.0f && pw * ROWS_PER_WARP + r < a.pr.Q) R_part += logf(mine + 1e-6f);  // KNRM.py:51-52
+        const float rsum = __shfl_sync(0xffffffffu, t, KT);
+        if (rsum != 0.0f && qrow < a.pr.Q) R_part += logf(t + 1e-6f);  // KNRM.py:51-52
       }
+      ps.release(s, ub, lane);
       float* part = sPart + (it & 1) * POOL_WARPS * KT;
       if (lane < KT) part[pw * KT + lane] = R_part;
-      epi_barrier();  // the 8 pooling warps.  part[] of this parity is rewritten two pairs (= two barriers) later
+      epi_barrier();  // part[] of this parity is rewritten two pairs (= at least two barriers) later
       if (pw == 0) {
         float R = 0.f;
         if (lane < a.K) {
@@ -122,7 +146,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
       }
     }
   }
-  teardown(s, tmem_base, tid);
+  teardown(s, tmem_base, tid, MMA_WARP_PIPE);
 }
 
 // hi/lo bf16 planes of the L2-normalised table (see table.cu for the fp32 variant)

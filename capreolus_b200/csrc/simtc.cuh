@@ -24,8 +24,9 @@
 // 32-63), warps 8-11 gather producers, warp 12 = MMA issuer + TMEM allocator (416 threads: PACRR, whose conv epilogue
 // needs the whole tile with its halo and runs drain -> conv sequentially on warps 0-7).
 // KNRM and DRMM pool column-additively, so they use the PIPELINED epilogue (544 threads): warps 0,1,4,5 only drain, into
-// two half-tile buffers of 32 x 256 cosines, and 8 pooling warps (2,3,6,7 + 13-16) consume them -- drain of half h+1
-// overlaps pooling of half h, across pair boundaries.
+// two half-tile buffers of 32 x 256 cosines, and 8 pooling warps consume them -- drain of half h+1 overlaps pooling of
+// half h, across pair boundaries.  A warp runs on sub-partition warp % 4 and pooling is MUFU / issue bound, so the roles
+// are laid out two pooling warps per sub-partition: pooling = 2,3,6,7,8,9,12,13; producers = 10,11,14,15; MMA = 16.
 #pragma once
 #include "simtile.cuh"
 #include "tc_common.cuh"
@@ -45,7 +46,9 @@ constexpr int D_STAGES = 2;                   // ring depth
 constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
 constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
 constexpr int POOL_WARPS = 8;                 // pipelined epilogue: pooling warps
-constexpr int THREADS_PIPE = THREADS + 4 * 32;  // + warps 13-16
+constexpr int THREADS_PIPE = THREADS + 4 * 32;  // 17 warps
+constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;  // sequential layout (PACRR)
+constexpr int MMA_WARP_PIPE = 16;                // pipelined layout
 constexpr int HALF_PITCH = NT_DOCS + 4;       // 260 floats: one-row-per-lane float4 stores are conflict-free (260 % 32 == 4)
 constexpr int HALF_FLOATS = QT * HALF_PITCH;  // one half tile = 33 280 B; two of them fit in the full-tile region
 constexpr int SPARE_FLOATS = SIM_ROWS * SIM_PITCH - 2 * HALF_FLOATS;  // 1 936 floats left over there (DRMM counters)
@@ -73,7 +76,9 @@ __host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes) {
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
   Smem s;
-  unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic instead of rounding the pointer as an integer: the compiler keeps the shared address space and
+  // emits LDS/STS instead of generic loads)
+  unsigned char* p = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   s.q0 = p;
   s.q_stride = atoms * Q_ATOM_BYTES;
   p += 2 * atoms * Q_ATOM_BYTES;
@@ -114,7 +119,7 @@ struct Problem {
 __device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
 
 // Common prologue: barriers + TMEM.  Call from all threads; returns the TMEM base.
-__device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads = THREADS) {
+__device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads = THREADS, int mma_warp = MMA_WARP) {
   const int warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -132,17 +137,17 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads =
     tc::fence_barrier_init();
   }
   for (int i = tid; i < SIM_ROWS * SIM_PITCH; i += nthreads) s.sim[i] = 0.f;
-  if (warp == EPI_WARPS + PROD_WARPS) tc::tmem_alloc(s.tmem_slot, 512);
+  if (warp == mma_warp) tc::tmem_alloc(s.tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   return *s.tmem_slot;
 }
 
-__device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int tid) {
+__device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int tid, int mma_warp = MMA_WARP) {
   tc::tc_fence_before();
   __syncthreads();
-  if ((tid >> 5) == EPI_WARPS + PROD_WARPS) {
+  if ((tid >> 5) == mma_warp) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -333,9 +338,14 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
 }
 
 // ---- pipelined epilogue (KNRM, DRMM) -----------------------------------------------------------------------------------
+// warp -> role.  Drain warps must sit on TMEM lane quarters 0 and 1 (warp % 4 in {0,1}); the rest is balanced per
+// sub-partition (warp % 4): SMSP0 = drain 0,4 + pool 8,12 + MMA 16; SMSP1 = drain 1,5 + pool 9,13; SMSP2 = pool 2,6 +
+// producers 10,14; SMSP3 = pool 3,7 + producers 11,15.
 __device__ __forceinline__ bool is_drain_warp(int warp) { return warp < 8 && (warp & 2) == 0; }
-__device__ __forceinline__ bool is_pool_warp(int warp) { return (warp < 8 && (warp & 2) != 0) || warp > EPI_WARPS + PROD_WARPS; }
-__device__ __forceinline__ int pool_index(int warp) { return warp < 8 ? ((warp >> 2) * 2 + (warp & 1)) : 4 + (warp - (EPI_WARPS + PROD_WARPS + 1)); }
+__device__ __forceinline__ bool is_pool_warp(int warp) { return warp < 16 && ((warp < 8) == ((warp & 2) != 0)); }
+__device__ __forceinline__ bool is_producer_warp(int warp) { return warp >= 8 && warp < 16 && (warp & 2) != 0; }
+__device__ __forceinline__ int pool_index(int warp) { return (warp >> 2) * 2 + (warp & 1); }      // 2,3,6,7,8,9,12,13 -> 0..7
+__device__ __forceinline__ int producer_index(int warp) { return ((warp - 8) >> 2) * 2 + (warp & 1); }  // 10,11,14,15 -> 0..3
 __device__ __forceinline__ float* half_tile(const Smem& s, int hb) { return s.sim + hb * HALF_FLOATS; }
 __device__ __forceinline__ float* spare_scratch(const Smem& s) { return s.sim + 2 * HALF_FLOATS; }
 
