@@ -22,6 +22,7 @@ namespace capr {
 
 constexpr int MAX_SLOTS = 64;     // nbins + 1 (FFMA engine)
 constexpr int MAX_SLOTS_TC = 32;  // nbins + 1 (tensor-core engine: shared memory is nearly full)
+constexpr int CNT_PITCH_TC = 33;  // counter row stride there: rows land in different banks for the same bin
 
 struct DrmmArgs {
   const long long* q;
@@ -85,6 +86,37 @@ __device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid
       const unsigned exact = __ballot_sync(0xffffffffu, real && v > 0.999f && v < 1.001f);  // DRMM.py:66
       if (lane == 0 && exact) c_row[a.nbins] += __popc(exact);
       __syncwarp();
+    }
+  }
+}
+
+// Tensor-core engine: lane = query row, warp = a 32-column slice of the half tile (the one-row-per-lane float4 reads are
+// conflict-free, the doc ids of the slice are warp-uniform broadcasts, so the padding test is a uniform branch).  All 8
+// slices add into the same per-row counters with shared-memory integer atomics: integer adds commute, so the result is
+// deterministic; the odd row stride puts equal bins of different rows in different banks.
+__device__ __forceinline__ void drmm_count_slice(const float* tile, int pitch, int col0, int nvalid, int qi, const int* did_slice,
+                                                 const DrmmArgs& a, const float* ub, int* cnt_row) {
+  const float guess_scale = 0.5f * (float)a.nbins;
+  const float4* row = reinterpret_cast<const float4*>(tile + (threadIdx.x & 31) * pitch + col0);
+  const int4* dids = reinterpret_cast<const int4*>(did_slice);
+  for (int g = 0; g < 8; ++g) {
+    if (g * 4 >= nvalid) break;  // warp-uniform
+    const float4 x = row[g];
+    const int4 d4 = dids[g];
+    const float vv[4] = {x.x, x.y, x.z, x.w};
+    const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (g * 4 + j >= nvalid || dd[j] == 0) continue;  // warp-uniform.  Padded columns are pushed to +1e7: no bin (DRMM.py:59)
+      const float v = vv[j];
+      // same binning as drmm_count_tile: arithmetic guess, one comparison on each side against the exact fp32 bounds
+      const int g0 = max(0, min((int)floorf((v + 1.0f) * guess_scale), a.nbins - 1));
+      const float hi = ub[g0];
+      const float lo = ub[max(g0 - 1, 0)];
+      int b = g0 + ((v >= hi) ? 1 : 0) - ((g0 > 0 && v < lo) ? 1 : 0);
+      if (v == 1.0f && qi > 0 && qi == dd[j]) b = a.nbins - 1;  // identical in-vocabulary tokens (see drmm_count_tile)
+      if (b < a.nbins) atomicAdd(cnt_row + b, 1);
+      if (v > 0.999f && v < 1.001f) atomicAdd(cnt_row + a.nbins, 1);  // DRMM.py:66
     }
   }
 }
@@ -179,9 +211,9 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
-  static_assert((QT * MAX_SLOTS_TC + MAX_SLOTS_TC + QT) <= SPARE_FLOATS, "DRMM scratch must fit behind the two half tiles");
-  int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][MAX_SLOTS_TC]
-  float* ub = reinterpret_cast<float*>(cnt + QT * MAX_SLOTS_TC);  // [MAX_SLOTS_TC]
+  static_assert((QT * CNT_PITCH_TC + MAX_SLOTS_TC + QT) <= SPARE_FLOATS, "DRMM scratch must fit behind the two half tiles");
+  int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][CNT_PITCH_TC]
+  float* ub = reinterpret_cast<float*>(cnt + QT * CNT_PITCH_TC);  // [MAX_SLOTS_TC]
   float* z = ub + MAX_SLOTS_TC;                                   // [QT]
   const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
   if (is_producer_warp(warp)) {
@@ -197,18 +229,18 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
     PoolSync ps;
     int unit = 0, it = 0;
     for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
-      for (int i = ptid; i < QT * MAX_SLOTS_TC; i += POOL_WARPS * 32) cnt[i] = 0;
+      for (int i = ptid; i < QT * CNT_PITCH_TC; i += POOL_WARPS * 32) cnt[i] = 0;
       epi_barrier();  // the 8 pooling warps: counters (and, first time, the bounds) are in place
-      const int* qid = s.qid + (it & 1) * QT;
       for (int h = 0; h < halves; ++h, ++unit) {
         const int ub_i = unit & 1;
-        ps.wait_full(s, ub_i);
-        drmm_count_tile<MAX_SLOTS_TC, HALF_PITCH, NT_DOCS>(half_tile(s, ub_i), qid, s.did + (it & 1) * DT + h * NT_DOCS,
-                                                           min(NT_DOCS, a.D - h * NT_DOCS), a, ub, cnt, pw, lane);
+        ps.wait_full(s, ub_i);  // also orders the drain warps' id writes of this pair before the reads below
+        const int qi = s.qid[(it & 1) * QT + lane];
+        drmm_count_slice(half_tile(s, ub_i), HALF_PITCH, pw * 32, min(NT_DOCS, a.D - h * NT_DOCS) - pw * 32, qi,
+                         s.did + (it & 1) * DT + h * NT_DOCS + pw * 32, a, ub, cnt + lane * CNT_PITCH_TC);
         ps.release(s, ub_i, lane);
       }
       epi_barrier();
-      drmm_finish<MAX_SLOTS_TC>(a, pair, cnt, z, pw, lane, EpiSync());
+      drmm_finish<CNT_PITCH_TC>(a, pair, cnt, z, pw, lane, EpiSync());
       epi_barrier();  // z / cnt are rewritten by the next pair
     }
   }
