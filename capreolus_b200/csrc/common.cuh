@@ -45,6 +45,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Packed fp32 FMA of sm_100 (FFMA2): {w,w} * b + c on both halves with one instruction.  With w coming from constant
+// memory ptxas emits the scalar-broadcast uniform-register form (FFMA2 R, R.F32x2, UR.F32, R.F32x2).
+__device__ __forceinline__ float2 fma2_bcast(float w, float2 b, float2 c) {
+  const float2 ww = make_float2(w, w);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(rd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&ww)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -52,41 +52,45 @@ __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ?
 
 // One n-gram module over the rows of this warp.  feat layout: [QT][qterm], this module writes columns
 // [col0, col0 + kmax).
-template <int N, int FT>
-__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane) {
+// The 4 query rows of the warp are convolved together and every lane takes TWO doc columns per step (c and c + 32),
+// packed in the two halves of FFMA2 operands: a filter tap (a uniform-register scalar, broadcast by the instruction)
+// feeds 4 FFMA2 = 8 multiply-adds, and the windows of the 4 rows share their shared-memory loads.
+template <int N, int FT, int KM, int R>
+__device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int q0, int lane) {
   constexpr int w_off = conv_w_slot(N), b_off = conv_b_slot(N);
-  constexpr int R = QT / (NT / 32);  // the 4 query rows of this warp are convolved together: every filter tap
-  const int q0 = warp * R;           // (a uniform-register operand) feeds 4 FFMAs, and the 4 windows share rows
-  if (q0 >= a.Q) return;             // warp-uniform
-  float top[R][MAX_KMAX];
+  if (q0 >= a.Q) return;  // warp-uniform
+  float top[R][KM];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int k = 0; k < MAX_KMAX; ++k) top[r][k] = -INFINITY;
-  for (int c = lane; c < a.D; c += 32) {
-    float win[R + N - 1][N];
+    for (int k = 0; k < KM; ++k) top[r][k] = -INFINITY;
+  for (int c = lane; c < a.D; c += 64) {
+    float2 win[R + N - 1][N];  // .x: column c, .y: column c + 32 (inside the zero halo when past the doc)
 #pragma unroll
     for (int u = 0; u < R + N - 1; ++u)
 #pragma unroll
-      for (int v = 0; v < N; ++v) win[u][v] = sim[(q0 + u) * SIM_PITCH + c + v];
-    float best[R];
+      for (int v = 0; v < N; ++v) {
+        const float* p = sim + (q0 + u) * SIM_PITCH + c + v;
+        win[u][v] = make_float2(p[0], p[32]);
+      }
+    float2 best[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) best[r] = -INFINITY;
+    for (int r = 0; r < R; ++r) best[r] = make_float2(-INFINITY, -INFINITY);
     auto one_filter = [&](int f) {
-      float x[R];
+      float2 x[R];
       const float bias = c_conv_b[b_off + f];
 #pragma unroll
-      for (int r = 0; r < R; ++r) x[r] = bias;
+      for (int r = 0; r < R; ++r) x[r] = make_float2(bias, bias);
 #pragma unroll
       for (int u = 0; u < N; ++u)
 #pragma unroll
         for (int v = 0; v < N; ++v) {
           const float w = c_conv_w[w_off + f * N * N + u * N + v];
 #pragma unroll
-          for (int r = 0; r < R; ++r) x[r] = fmaf(w, win[r + u][v], x[r]);
+          for (int r = 0; r < R; ++r) x[r] = fma2_bcast(w, win[r + u][v], x[r]);
         }
 #pragma unroll
-      for (int r = 0; r < R; ++r) best[r] = fmaxf(best[r], x[r]);
+      for (int r = 0; r < R; ++r) best[r] = make_float2(fmaxf(best[r].x, x[r].x), fmaxf(best[r].y, x[r].y));
     };
     if (FT > 0) {
 #pragma unroll
@@ -94,15 +98,20 @@ __device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a,
     } else {
       for (int f = 0; f < F; ++f) one_filter(f);
     }
+    const bool second = c + 32 < a.D;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float v = fmaxf(best[r], 0.f);  // ReLU (PACRR.py:78) commutes with the filter max (PACRR.py:79)
 #pragma unroll
-      for (int k = 0; k < MAX_KMAX; ++k) {  // insert into the lane-local descending top-k
-        if (k < a.kmax && v > top[r][k]) {
-          const float t = top[r][k];
-          top[r][k] = v;
-          v = t;
+      for (int half = 0; half < 2; ++half) {
+        // ReLU (PACRR.py:78) commutes with the filter max (PACRR.py:79)
+        float v = half == 0 ? fmaxf(best[r].x, 0.f) : (second ? fmaxf(best[r].y, 0.f) : -INFINITY);
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {  // insert into the lane-local descending top-k
+          if (k < a.kmax && v > top[r][k]) {
+            const float t = top[r][k];
+            top[r][k] = v;
+            v = t;
+          }
         }
       }
     }
@@ -116,23 +125,41 @@ __device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a,
       const unsigned owners = __ballot_sync(0xffffffffu, top[r][0] == m);
       if (lane == (__ffs(owners) - 1)) {
 #pragma unroll
-        for (int j = 0; j < MAX_KMAX - 1; ++j) top[r][j] = top[r][j + 1];
-        top[r][MAX_KMAX - 1] = -INFINITY;
+        for (int j = 0; j < KM - 1; ++j) top[r][j] = top[r][j + 1];
+        top[r][KM - 1] = -INFINITY;
       }
       if (lane == 0) feat[(q0 + r) * qterm + col0 + k] = m;
     }
   }
 }
 
+// 4 rows at a time for the windows the reference uses (n <= 3); 2 + 2 for the larger ones (register budget)
+template <int N, int FT, int KM>
+__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane) {
+  constexpr int ROWS = QT / (NT / 32);
+  if (N <= 3) {
+    ngram_rows<N, FT, KM, ROWS>(sim, a, F, feat, qterm, col0, warp * ROWS, lane);
+  } else {
+    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS, lane);
+    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS + ROWS / 2, lane);
+  }
+}
+
+template <int FT, int KM>
+__device__ __forceinline__ void ngram_dispatch_n(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane) {
+  switch (n) {
+    case 1: ngram_pass<1, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 2: ngram_pass<2, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 3: ngram_pass<3, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 4: ngram_pass<4, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    default: ngram_pass<5, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+  }
+}
+
 template <int FT>
 __device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane) {
-  switch (n) {
-    case 1: ngram_pass<1, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 2: ngram_pass<2, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 3: ngram_pass<3, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 4: ngram_pass<4, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    default: ngram_pass<5, FT>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-  }
+  if (a.kmax <= 2) ngram_dispatch_n<FT, 2>(n, s, a, feat, qterm, col0, warp, lane);  // the reference default (kmax = 2)
+  else ngram_dispatch_n<FT, MAX_KMAX>(n, s, a, feat, qterm, col0, warp, lane);
 }
 
 // Everything after the cosine tile: n-gram conv/max/top-k passes, softmax(idf) channel, 3-layer combine MLP.

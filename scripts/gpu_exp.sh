@@ -10,4 +10,3 @@ b() {
 b knrm tc; b drmm tc; b pacrr tc
 CAPR_DEBUG_FLAGS=0x300 b knrm skip_pool_drain
 CAPR_DEBUG_FLAGS=0x100 b knrm skip_pool
-CAPR_DEBUG_FLAGS=0x200 b knrm skip_drain_stores
