@@ -38,7 +38,7 @@ BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
 MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP"}
 DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024}
 DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256}
-TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_kernel)"}
+TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)"}
 
 
 class Extractor:
@@ -290,9 +290,9 @@ def main():
             achieved = BERT_FLOPS_PER_PAIR * n / (kernel_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
                     "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)", "kernel": TOP_KERNEL["bert"],
-                    "algorithmic_flops_per_pair": BERT_FLOPS_PER_PAIR, "issued_tensor_flops_per_pair": 3 * 12 * 2 * 12 * 768 * 768 * 512,
+                    "algorithmic_flops_per_pair": BERT_FLOPS_PER_PAIR, "issued_tensor_flops_per_pair": 3 * BERT_FLOPS_PER_PAIR,
                     "note": "achieved counts ALGORITHMIC flops over the whole forward; the bf16x3 parity mode issues 3 tensor-core products per "
-                            "Linear-layer flop and attention runs in fp32 FFMA (v1)", "forward_ms": kernel_ms, "pairs_per_forward": n}
+                            "algorithmic flop (Linear layers and attention)", "forward_ms": kernel_ms, "pairs_per_forward": n}
             launches = args.steps * (2 + 12 * 7) * ((n + 127) // 128)
             workload = (f"monoBERT (BERT-base, random init) forward, {n} synthetic pairs per GPU per step, L={BERT_L} (|q|={Q}, doc truncated to "
                         f"{BERT_L - Q - 3}), bf16x3 parity mode; bounded sample of BASELINE.json configs[3] (1000 q x 1000 docs)")

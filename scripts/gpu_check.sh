@@ -34,7 +34,7 @@ for f in ["gpurun_out/launches_knrm.csv", "gpurun_out/launches_bert.csv"]:
 PY
 fi
 if [ "$1" == "full" ]; then
-echo "== ncu full capture (knrm_kernel, 14800 pairs)"
+echo "== ncu full capture (knrm_tc_kernel, 14800 pairs)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:knrm_tc_kernel -s 3 -c 1 -f -o gpurun_out/knrm_tc_full \
    python bench.py --pairs 14800 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
