@@ -176,6 +176,80 @@ def make_pacrr():
         print("pacrr", shape_name, out["default/pos"][:4])
 
 
+def make_drmmtks():
+    """the reference DRMMTKS wrapper (reranker/DRMMTKS.py) on the parity inputs."""
+    ref = refshim.load_rerankers()
+    for shape_name in SHAPES:
+        table, batch = _inputs(shape_name)
+        B, Q, D, V, E, *_ = SHAPES[shape_name]
+        tb = _t(batch)
+        out = _common(shape_name, table, batch)
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        for variant, cfg in {
+            "default": dict(topk=10, gateType="IDF", freezeemb=True),
+            "k3": dict(topk=3, gateType="IDF", freezeemb=True),
+            "k20": dict(topk=20, gateType="IDF", freezeemb=False),
+        }.items():
+            torch.manual_seed(400)
+            rr = ref.DRMMTKS.DRMMTKS(cfg, provide={"extractor": ext})
+            model = rr.build_model().eval()
+            with torch.no_grad():
+                # default init (|w| <= 0.1 / 0.01) makes every score ~bias: spread the weights (as for DRMM above)
+                model.ffw[0].weight.mul_(10.0)
+                model.gates.weight.mul_(40.0)
+                pos, neg = rr.score(tb)
+                assert torch.equal(rr.test(tb), pos)
+                if variant == "default":
+                    out["topk"] = torch.topk(model.simmat(tb["query"], tb["posdoc"]), k=10, dim=-1)[0].numpy()
+            out[f"{variant}/pos"] = pos.numpy()
+            out[f"{variant}/neg"] = neg.numpy()
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model).items()})
+        np.savez_compressed(GOLDEN / f"drmmtks_{shape_name}.npz", **out)
+        print("drmmtks", shape_name, out["default/pos"][:4])
+
+
+def make_convknrm():
+    """the reference ConvKNRM wrapper (reranker/ConvKNRM.py) on the parity inputs
+    (no OOV ids: ConvKNRM.py:44-45 indexes the table with the raw ids)."""
+    ref = refshim.load_rerankers()
+    for shape_name in SHAPES:
+        table, batch = _inputs(shape_name, oov=False)
+        B, Q, D, V, E, *_ = SHAPES[shape_name]
+        tb = _t(batch)
+        out = _common(shape_name, table, batch)
+        ext = refshim.FakeExtractor(table, maxqlen=Q, maxdoclen=D)
+        for variant, cfg in {
+            "default": dict(gradkernels=True, maxngram=3, crossmatch=True, filters=128, scoretanh=False, singlefc=True),
+            "nocross_twofc": dict(gradkernels=True, maxngram=2, crossmatch=False, filters=48, scoretanh=False, singlefc=False),
+            "uni_tanh": dict(gradkernels=False, maxngram=1, crossmatch=True, filters=128, scoretanh=True, singlefc=True),
+        }.items():
+            torch.manual_seed(500)
+            rr = ref.ConvKNRM.ConvKNRM(cfg, provide={"extractor": ext})
+            model = rr.build_model().eval()
+            with torch.no_grad():
+                # untrained features are O(100) per kernel x 9 views: scale the first combine layer so that tanh variants
+                # do not saturate and the default score is O(1..10)
+                model.combine[0].weight.mul_(0.05)
+                if variant == "default" and shape_name != "full":
+                    for i, k in enumerate(model.kernels.kernels):
+                        k.mu.add_(0.011 * (i - 4))
+                        k.sigma.mul_(1.0 + 0.04 * i)
+                pos, neg = rr.score(tb)
+                assert torch.equal(rr.test(tb), pos)
+                if variant == "default":
+                    # the [B,99] tensor fed to `combine`: recompute it with a hook on the combine layer's input
+                    grabbed = []
+                    h = model.combine[0].register_forward_hook(lambda m, i, o: grabbed.append(i[0].detach().clone()))
+                    rr.test(tb)
+                    h.remove()
+                    out["feats"] = grabbed[0].numpy()
+            out[f"{variant}/pos"] = pos.numpy()
+            out[f"{variant}/neg"] = neg.numpy()
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model, skip=("embeddings.weight",)).items()})
+        np.savez_compressed(GOLDEN / f"convknrm_{shape_name}.npz", **out)
+        print("convknrm", shape_name, out["default/pos"][:4])
+
+
 BERT_CONFIGS = {
     # name: (BertConfig kwargs, N docs, P passages, L, qlen, weight seed, input seed)
     "tiny": (dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, vocab_size=1000,
@@ -294,7 +368,7 @@ def make_losses():
                         hinge=ref.common.pair_hinge_loss([tp, tn]).numpy(), softmax=ref.common.pair_softmax_loss([tp, tn]).numpy())
 
 
-ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
+ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "drmmtks": make_drmmtks, "convknrm": make_convknrm, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)

@@ -194,6 +194,89 @@ def pacrr_forward(state: dict, table, doc, query, query_idf, mingram=1, maxgram=
 
 
 # --------------------------------------------------------------------------------------------------
+# DRMMTKS   (reranker/DRMMTKS.py:50-63)   -- SURVEY.md §8(f) rank 1
+# --------------------------------------------------------------------------------------------------
+def drmmtks_topk(table, doc, query, topk=10) -> torch.Tensor:
+    """``torch.topk(cos_mat, k, dim=-1)`` of DRMMTKS.py:55-56 -> ``[B,Q,k]`` (descending; zeros of padded columns compete)."""
+    sim = similarity_matrix(table, query, doc)
+    top, _ = torch.topk(sim, k=topk, dim=-1)
+    return top
+
+
+def drmmtks_forward(state: dict, table, doc, query, query_idf, topk=10) -> torch.Tensor:
+    """``DRMMTKS_class.forward(doc, query, query_idf)`` with ``gateType='IDF'`` (reranker/DRMMTKS.py:50-63) -> ``[B,1]``.
+
+    (``gateType='TV'`` passes the int64 token ids to a Linear(E,1), DRMMTKS.py:59,43 -- it raises in the reference.)"""
+    B, Q = query.shape
+    q_mask = (query != 0).float()
+    top = drmmtks_topk(table, doc, query, topk)
+    z = torch.tanh(F.linear(top, state["ffw.0.weight"], state["ffw.0.bias"])).reshape(B, Q)
+    gate = F.linear(query_idf.float()[:, :, None], state["gates.weight"]).reshape(B, Q) + (1 - q_mask) * -1e7
+    w = F.softmax(gate, dim=1)
+    x = (w * z).sum(dim=-1, keepdim=True)
+    return F.linear(x, state["output_layer.weight"], state["output_layer.bias"])
+
+
+# --------------------------------------------------------------------------------------------------
+# ConvKNRM   (reranker/ConvKNRM.py:43-77, StackedSimilarityMatrix reranker/common.py:187-221)   -- SURVEY.md §8(f) rank 1
+# --------------------------------------------------------------------------------------------------
+def convknrm_ngram_reps(state: dict, table, toks, maxngram=3):
+    """``conv[layer](pad(emb.permute(0,2,1))).permute(0,2,1)`` for n = 1..maxngram (ConvKNRM.py:47-50): list of ``[B,L,F]``.
+    Conv1d(E, F, n) over the sequence zero-padded by n-1 on the right; no activation."""
+    emb = F.embedding(toks, table).permute(0, 2, 1)
+    reps = []
+    for n in range(1, maxngram + 1):
+        x = F.pad(emb, (0, n - 1), value=0.0) if n > 1 else emb
+        reps.append(F.conv1d(x, state[f"convs.{n - 1}.0.weight"], state[f"convs.{n - 1}.0.bias"]).permute(0, 2, 1))
+    return reps
+
+
+def stacked_similarity(a, b, q_tok, d_tok, padding=0) -> torch.Tensor:
+    """One cosine view of ``StackedSimilarityMatrix.forward`` (common.py:202-217) -> ``[B,1,Q,D]``."""
+    a_den = a.norm(p=2, dim=2)[:, :, None] + 1e-9
+    b_den = b.norm(p=2, dim=2)[:, None, :] + 1e-9
+    sim = a.bmm(b.permute(0, 2, 1)) / (a_den * b_den)
+    sim = torch.where((q_tok == padding)[:, :, None], torch.zeros_like(sim), sim)
+    sim = torch.where((d_tok == padding)[:, None, :], torch.zeros_like(sim), sim)
+    return sim[:, None]
+
+
+def convknrm_features(state: dict, table, doc, query, maxngram=3, crossmatch=True, mus=None, sigmas=None) -> torch.Tensor:
+    """The ``[B, K*VIEWS]`` tensor fed to ``combine`` (ConvKNRM.py:64-76); feature index = k * VIEWS + view,
+    view = nq * maxngram + nd with crossmatch."""
+    mus = KNRM_MUS if mus is None else mus
+    sigmas = KNRM_SIGMAS if sigmas is None else sigmas
+    a_reps = convknrm_ngram_reps(state, table, query, maxngram)
+    b_reps = convknrm_ngram_reps(state, table, doc, maxngram)
+    if crossmatch:
+        views = [stacked_similarity(a, b, query, doc) for a in a_reps for b in b_reps]
+    else:
+        views = [stacked_similarity(a, b, query, doc) for a, b in zip(a_reps, b_reps)]
+    simmats = torch.cat(views, dim=1)  # [B,VIEWS,Q,D]
+    kernels = torch.stack([torch.exp(-0.5 * (simmats - m) * (simmats - m) / s / s) for m, s in zip(mus, sigmas)], dim=1)
+    BATCH, KERNELS, VIEWS, QLEN, DLEN = kernels.shape
+    kernels = kernels.reshape(BATCH, KERNELS * VIEWS, QLEN, DLEN)
+    sim_rep = simmats.reshape(BATCH, 1, VIEWS, QLEN, DLEN).expand(BATCH, KERNELS, VIEWS, QLEN, DLEN).reshape(BATCH, KERNELS * VIEWS, QLEN, DLEN)
+    result = kernels.sum(dim=3)
+    mask = sim_rep.sum(dim=3) != 0.0
+    result = torch.where(mask, (result + 1e-6).log(), mask.float())
+    return result.sum(dim=2)
+
+
+def convknrm_forward(state: dict, table, doc, query, query_idf=None, maxngram=3, crossmatch=True, singlefc=True,
+                     scoretanh=False) -> torch.Tensor:
+    """``ConvKNRM_class.forward(sentence, query_sentence, query_idf)`` (reranker/ConvKNRM.py:43-77) -> ``[B,1]``."""
+    p = knrm_params_from_state(state)
+    x = convknrm_features(state, table, doc, query, maxngram, crossmatch, p["mus"], p["sigmas"])
+    if singlefc:
+        x = F.linear(x, state["combine.0.weight"], state["combine.0.bias"])
+    else:
+        x = torch.tanh(F.linear(x, state["combine.0.weight"], state["combine.0.bias"]))
+        x = F.linear(x, state["combine.2.weight"], state["combine.2.bias"])
+    return torch.tanh(x) if scoretanh else x
+
+
+# --------------------------------------------------------------------------------------------------
 # losses   (reranker/common.py:7,96-103)
 # --------------------------------------------------------------------------------------------------
 def pair_hinge_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:

@@ -157,3 +157,44 @@ def test_live_reference_agrees_with_goldens():
     with torch.no_grad():
         pos = rr.test(_tb(g))
     np.testing.assert_allclose(pos.numpy(), g["default/pos"], rtol=1e-5, atol=1e-5)
+
+
+# ---- DRMMTKS, ConvKNRM ---------------------------------------------------------------------
+DRMMTKS_VARIANTS = {"default": 10, "k3": 3, "k20": 20}
+CONVKNRM_VARIANTS = {
+    "default": dict(maxngram=3, crossmatch=True, singlefc=True, scoretanh=False),
+    "nocross_twofc": dict(maxngram=2, crossmatch=False, singlefc=False, scoretanh=False),
+    "uni_tanh": dict(maxngram=1, crossmatch=True, singlefc=True, scoretanh=True),
+}
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("variant", list(DRMMTKS_VARIANTS))
+def test_drmmtks_scores(shape, variant):
+    g = load_golden(f"drmmtks_{shape}")
+    table = torch.from_numpy(golden_table(g))
+    tb = _tb(g)
+    st = golden_state(g, variant)
+    k = DRMMTKS_VARIANTS[variant]
+    for side, doc in (("pos", "posdoc"), ("neg", "negdoc")):
+        got = restated.drmmtks_forward(st, table, tb[doc], tb["query"], tb["query_idf"], topk=k).view(-1).numpy()
+        assert rel_err(got, g[f"{variant}/{side}"]) < TOL
+    if variant == "default":
+        np.testing.assert_allclose(restated.drmmtks_topk(table, tb["posdoc"], tb["query"], 10).numpy(), g["topk"], atol=2e-6)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("variant", list(CONVKNRM_VARIANTS))
+def test_convknrm_scores(shape, variant):
+    g = load_golden(f"convknrm_{shape}")
+    table = torch.from_numpy(golden_table(g))
+    tb = _tb(g)
+    st = golden_state(g, variant)
+    kw = CONVKNRM_VARIANTS[variant]
+    for side, doc in (("pos", "posdoc"), ("neg", "negdoc")):
+        got = restated.convknrm_forward(st, table, tb[doc], tb["query"], tb["query_idf"], **kw).view(-1).numpy()
+        assert rel_err(got, g[f"{variant}/{side}"]) < TOL * 10
+    if variant == "default":
+        kp = restated.knrm_params_from_state(st)
+        feats = restated.convknrm_features(st, table, tb["posdoc"], tb["query"], 3, True, kp["mus"], kp["sigmas"]).numpy()
+        np.testing.assert_allclose(feats, g["feats"], rtol=1e-4, atol=1e-3)
