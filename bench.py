@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W                 # one rank per GPU, weak scaling + NCCL score gather
     python bench.py --impl reference --steps 3 --warmup 1         # the reference's CPU PyTorch path (oracle port) on host cores
-    python bench.py --model bert | drmm | pacrr                   # the other configs of BASELINE.json (not the headline line)
+    python bench.py --model bert | drmm | pacrr | drmmtks | convknrm   # the other configs of BASELINE.json (not the headline line)
 
 A "step" is one pass of the hot path over one batch of synthetic (query, doc) pairs per GPU: ``reranker.test(batch)``
 -> C ABI -> fused kernel(s) (+ one all-gather of the scores when N > 1).  Prints ONE JSON line (rank 0).
@@ -35,10 +35,12 @@ ALGO_BYTES_PER_PAIR = (Q + D) * 8 + (Q + D) * E * 4 + 4
 BERT_L = 512
 # per layer 2*12*768^2*512 (Linear layers) + 2*2*512^2*768 (attention) = 8.05 GFLOP; x12 layers = 96.6 GFLOP
 BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
-MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP"}
-DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024}
-DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256}
-TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)"}
+MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM"}
+DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000}
+DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500}
+TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)",
+              "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
+ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
 
 
 class Extractor:
@@ -137,7 +139,7 @@ def cpu_reference_step(model_key, state):
             return 8
 
         return step, "HF BertForSequenceClassification(BertConfig()) random init, B=8, L=512, eval/no_grad (the module ptBERTMaxP.py:82 calls)"
-    fn = getattr(restated, {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward"}[model_key])
+    fn = getattr(restated, ORACLE_FN[model_key])
     table = torch.from_numpy(synthetic.embedding_table(V, E, seed=0))
     t = host_batch(model_key, 512, seed=2)
     pos = [0]
@@ -306,7 +308,7 @@ def main():
             roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": traffic,
                     "peak_source": pk["src"] + " hbm_gbs", "kernel": TOP_KERNEL[args.model], "kernel_ms_per_launch": kernel_ms,
                     "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "pairs_per_launch": n}
-            launches = args.steps
+            launches = args.steps * (1 if args.model != "convknrm" else 13 * ((n + 4095) // 4096))  # ConvKNRM: zero row, 2 rep kernels, 9 views, combine per chunk
             workload = (f"{MODELS[args.model]} forward, {n} synthetic pairs per GPU per step (BASELINE.json configs[1]), |q|={Q} |d|={D} vocab={V} "
                         f"emb={E}, zipf ids, random-init weights")
             l2 = "inputs larger than L2 (435 MB of ids per step); the 36 MB embedding table is L2-resident by design"

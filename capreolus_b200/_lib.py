@@ -55,6 +55,13 @@ SIGNATURES = {
     "capr_pacrr_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    POINTER(c_void_p), POINTER(c_void_p), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_int, c_int,
                                    _f32p, _f32p, c_void_p]),
+    "capr_drmmtks_forward_tc": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _f32p, _f32p,
+                                        _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_convknrm_proj_cols": (c_int, [c_int, c_int]),
+    "capr_convknrm_project": (c_int, [_f32p, c_int, c_int, POINTER(c_void_p), c_int, c_int, _f32p, c_void_p]),
+    "capr_convknrm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "capr_convknrm_forward": (c_int, [_i64p, _i64p, c_int, c_int, c_int, _f32p, c_int, c_int, c_int, POINTER(c_void_p), c_int, _f32p, _f32p, c_int,
+                                      _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
     "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),
     "capr_bert_create": (c_int, [POINTER(BertConfigStruct), POINTER(c_void_p), c_int, c_int, c_void_p, POINTER(c_void_p)]),

@@ -55,5 +55,7 @@ from capreolus_b200.reranker.KNRM import KNRM, KNRM_class  # noqa: E402,F401
 from capreolus_b200.reranker.DRMM import DRMM, DRMM_class  # noqa: E402,F401
 from capreolus_b200.reranker.PACRR import PACRR, PACRR_class  # noqa: E402,F401
 from capreolus_b200.reranker.ptBERTMaxP import PTBERTMaxP, PTBERTMaxP_Class  # noqa: E402,F401
+from capreolus_b200.reranker.DRMMTKS import DRMMTKS, DRMMTKS_class  # noqa: E402,F401
+from capreolus_b200.reranker.ConvKNRM import ConvKNRM, ConvKNRM_class  # noqa: E402,F401
 
-__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class"]
+__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class", "DRMMTKS", "DRMMTKS_class", "ConvKNRM", "ConvKNRM_class"]

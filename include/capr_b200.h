@@ -136,6 +136,41 @@ int capr_pacrr_forward_tc(const int64_t* query, const int64_t* doc, const float*
                           const float* l1b, const float* l2w, const float* l2b, const float* l3w, const float* l3b,
                           int combine, int nonlin, float* scores, float* topk_out, capr_stream_t stream);
 
+/* ---- DRMMTKS ------------------------------------------------------------------
+ * DRMMTKS_class.forward (capreolus/reranker/DRMMTKS.py:50-63): cosine matrix -> torch.topk(k) over the doc axis per query
+ * term -> ffw = Linear(k,1)+tanh -> IDF softmax term gate (DRMMTKS.py:32-48) -> output_layer.  Tensor-core engine only
+ * (table as bf16 hi/lo planes, capr_table_prepare_bf16).  gateType='TV' is not offered: the reference feeds int64 token
+ * ids to a Linear(E,1) there and raises.
+ *   ffw_w [1,topk], ffw_b [1], gate_w [1], out_w [1], out_b [1];  idf [B,Q];  topk_out [B,Q,topk] (nullable, descending).
+ * Limits: Q <= 32, D <= 512, pitch <= 320, topk <= min(32, D). */
+int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D, const void* table_hi,
+                            const void* table_lo, int V, int E, int pitch, int topk, const float* ffw_w, const float* ffw_b,
+                            const float* gate_w, const float* out_w, const float* out_b, float* scores, float* topk_out,
+                            capr_stream_t stream);
+
+/* ---- ConvKNRM -----------------------------------------------------------------
+ * ConvKNRM_class.forward (capreolus/reranker/ConvKNRM.py:43-77) with StackedSimilarityMatrix (common.py:187-221) and
+ * RbfKernelBank.  The embedding is frozen (ConvKNRM.py:18) and Conv1d is linear, so the n-gram encoders are folded into
+ * PROJECTED TABLES once per weight version:
+ *   capr_convknrm_project: proj [V, S*F] fp32, S = maxngram(maxngram+1)/2, column block slot(n,u) = n(n-1)/2 + u holds
+ *   emb . convs.{n-1}.0.weight[:, :, u]^T   (conv_w: HOST array of maxngram DEVICE pointers, weight [F,E,n]).
+ * capr_convknrm_forward then needs per token only row gathers + adds:  conv_n(t) = bias_n + sum_u proj[tok[t+u]][slot(n,u)].
+ *   conv_b: HOST array of maxngram DEVICE pointers (convs.{n-1}.0.bias [F]);  crossmatch: 1 = all maxngram^2 (nq, nd) views,
+ *   0 = nq == nd only;  mu, sigma [K];  w1 [H, K*VIEWS], b1 [H] (H = 1 when hidden == 0), w2 [1,hidden], b2 [1];
+ *   flags: CAPR_KNRM_SCORETANH;  feats_out [B, K*VIEWS] (nullable) = the tensor fed to `combine`, index k*VIEWS + view.
+ *   workspace: capr_convknrm_workspace_bytes(chunk, ...) bytes for `chunk` pairs at a time (any chunk >= 1 works; the
+ *   call loops over as many pairs as fit), 256-byte aligned.
+ * Token ids: 0 = <pad> (extractor.pad, ConvKNRM.py:17); ids < 0 or >= V make the reference raise IndexError -- here they
+ * contribute a zero vector.  Limits: Q <= 32, D <= 512, F % 4 == 0, F <= 320, maxngram <= 4, K <= 16. */
+int capr_convknrm_proj_cols(int maxngram, int F);
+int capr_convknrm_project(const float* emb /*[V,E]*/, int V, int E, const float* const* conv_w, int maxngram, int F,
+                          float* proj /*[V, capr_convknrm_proj_cols]*/, capr_stream_t stream);
+size_t capr_convknrm_workspace_bytes(int chunk, int Q, int D, int maxngram, int F, int K, int crossmatch);
+int capr_convknrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* proj, int V, int maxngram,
+                          int F, const float* const* conv_b, int crossmatch, const float* mu, const float* sigma, int K,
+                          const float* w1, const float* b1, int hidden, const float* w2, const float* b2, int flags,
+                          float* scores, float* feats_out, void* workspace, size_t workspace_bytes, capr_stream_t stream);
+
 /* ---- pairwise losses (tests / training loop) ------------------------------------------------------
  * pair_hinge_loss (capreolus/reranker/common.py:7,101-103): loss[0] = mean(max(0, 1 - (pos - neg))),
  * grad_pos/grad_neg [B] (nullable) = d loss / d score. */

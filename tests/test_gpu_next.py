@@ -1,0 +1,135 @@
+"""GPU parity for the SURVEY.md §8(f) rank-1 models, DRMMTKS and ConvKNRM: the CUDA path (through the C ABI) against the
+goldens the unmodified reference produced and against the pinned CPU oracle on fresh seeded inputs.  Tolerance 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state, golden_table, load_golden, rel_err
+from test_gpu_parity import DEV, SHAPES, TOL, Extractor, _batch, _build, _fresh
+
+pytestmark = pytest.mark.gpu
+
+DRMMTKS_CFG = {
+    "default": dict(topk=10, gateType="IDF", freezeemb=True),
+    "k3": dict(topk=3, gateType="IDF", freezeemb=True),
+    "k20": dict(topk=20, gateType="IDF", freezeemb=False),
+}
+CONVKNRM_CFG = {
+    "default": dict(gradkernels=True, maxngram=3, crossmatch=True, filters=128, scoretanh=False, singlefc=True),
+    "nocross_twofc": dict(gradkernels=True, maxngram=2, crossmatch=False, filters=48, scoretanh=False, singlefc=False),
+    "uni_tanh": dict(gradkernels=False, maxngram=1, crossmatch=True, filters=128, scoretanh=True, singlefc=True),
+}
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("variant", list(DRMMTKS_CFG))
+def test_drmmtks_scores_match_reference(shape, variant):
+    g = load_golden(f"drmmtks_{shape}")
+    rr, model = _build("DRMMTKS", g, variant, DRMMTKS_CFG[variant])
+    b = _batch(g)
+    with torch.no_grad():
+        pos, neg = rr.score(b)
+        assert torch.equal(rr.test(b), pos)
+    assert pos.shape == (g["query"].shape[0],)
+    assert rel_err(pos.cpu().numpy(), g[f"{variant}/pos"]) < TOL
+    assert rel_err(neg.cpu().numpy(), g[f"{variant}/neg"]) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_drmmtks_topk_matches_reference(shape):
+    g = load_golden(f"drmmtks_{shape}")
+    rr, model = _build("DRMMTKS", g, "default", DRMMTKS_CFG["default"])
+    b = _batch(g)
+    with torch.no_grad():
+        top = model.topk_similarities(b["posdoc"], b["query"]).cpu().numpy()
+    assert top.shape == g["topk"].shape
+    assert np.all(np.diff(top, axis=2) <= 0)  # descending, like torch.topk
+    np.testing.assert_allclose(top, g["topk"], atol=3e-6)
+
+
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 10, 50, 16)])
+def test_drmmtks_fresh_shapes(B, Q, D, V, E):
+    got, want = _fresh("DRMMTKS", "drmmtks_forward", DRMMTKS_CFG["default"], B, Q, D, V, E, seed=61)
+    assert rel_err(got, want) < TOL
+
+
+def test_drmmtks_errors():
+    from capreolus_b200 import reranker as R, synthetic
+
+    table = synthetic.embedding_table(100, 32, seed=0)
+    q = torch.ones(2, 8, dtype=torch.long, device=DEV)
+    d = torch.ones(2, 16, dtype=torch.long, device=DEV)
+    idf = torch.zeros(2, 8, device=DEV)
+    with torch.no_grad():
+        tv = R.DRMMTKS(dict(gateType="TV"), provide={"extractor": Extractor(table, 8, 16)}).build_model().to(DEV).eval()
+        with pytest.raises(ValueError, match="gateType"):
+            tv(d, q, idf)
+        big = R.DRMMTKS(dict(topk=17), provide={"extractor": Extractor(table, 8, 16)}).build_model().to(DEV).eval()
+        with pytest.raises(ValueError, match="topk"):  # torch.topk raises in the reference when k > maxdoclen
+            big(d, q, idf)
+        ok = R.DRMMTKS(provide={"extractor": Extractor(table, 8, 16)}).build_model().to(DEV).eval()
+        assert ok(d[:0], q[:0], idf[:0]).shape == (0, 1)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("variant", list(CONVKNRM_CFG))
+def test_convknrm_scores_match_reference(shape, variant):
+    g = load_golden(f"convknrm_{shape}")
+    rr, model = _build("ConvKNRM", g, variant, CONVKNRM_CFG[variant])
+    b = _batch(g)
+    with torch.no_grad():
+        pos, neg = rr.score(b)
+        assert torch.equal(rr.test(b), pos)
+    assert pos.shape == (g["query"].shape[0],)
+    if variant == "uni_tanh":  # tanh output: compare absolutely
+        np.testing.assert_allclose(pos.cpu().numpy(), g[f"{variant}/pos"], atol=1e-3)
+        np.testing.assert_allclose(neg.cpu().numpy(), g[f"{variant}/neg"], atol=1e-3)
+        return
+    assert rel_err(pos.cpu().numpy(), g[f"{variant}/pos"], floor=1e-2) < TOL
+    assert rel_err(neg.cpu().numpy(), g[f"{variant}/neg"], floor=1e-2) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_convknrm_features_match_reference(shape):
+    g = load_golden(f"convknrm_{shape}")
+    rr, model = _build("ConvKNRM", g, "default", CONVKNRM_CFG["default"])
+    b = _batch(g)
+    with torch.no_grad():
+        feats = model.kernel_features(b["posdoc"], b["query"]).cpu().numpy()
+    assert feats.shape == g["feats"].shape
+    assert rel_err(feats, g["feats"], floor=1e-1) < TOL
+
+
+def test_convknrm_chunked_equals_whole(monkeypatch):
+    """The rep table is staged chunk by chunk: a 7-pair chunk must give bit-identical scores to one 64-pair chunk."""
+    import capreolus_b200.reranker.ConvKNRM as M
+
+    g = load_golden("convknrm_full")
+    b = _batch(g)
+    rr, model = _build("ConvKNRM", g, "default", CONVKNRM_CFG["default"])
+    with torch.no_grad():
+        whole = rr.test(b)
+        monkeypatch.setattr(M, "CHUNK", 7)
+        model._ws = None
+        chunked = rr.test(b)
+    assert torch.equal(whole, chunked)
+
+
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 2, 50, 16)])
+def test_convknrm_fresh_shapes(B, Q, D, V, E):
+    got, want = _fresh("ConvKNRM", "convknrm_forward", CONVKNRM_CFG["default"], B, Q, D, V, E, seed=71, oov=False)
+    assert rel_err(got, want, floor=1e-2) < TOL
+
+
+def test_convknrm_projection_follows_weight_updates():
+    """The projected tables are derived data: an in-place change of a conv weight must be picked up by the next call."""
+    g = load_golden("convknrm_small")
+    rr, model = _build("ConvKNRM", g, "default", CONVKNRM_CFG["default"])
+    b = _batch(g)
+    with torch.no_grad():
+        s0 = rr.test(b).clone()
+        model.convs[1][0].weight.mul_(-1.0)
+        s1 = rr.test(b)
+        assert not torch.equal(s0, s1)
+        model.convs[1][0].weight.mul_(-1.0)
+        assert torch.equal(rr.test(b), s0)
