@@ -22,24 +22,30 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int M, int N, int n_m
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 32) {
+  if (warp == 1) {
+    // warp-uniform loop, one elected lane issues (the pattern of simtc::mma_loop): a divergent `if (lane == 0)` issuer
+    // measures ~150 cycles per instruction of issue overhead instead of the tensor pipe
     const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, M, N);
     const uint32_t a = tc::smem_u32(smem), b = a + 16384;
+    const uint64_t adesc = tc::make_sw128_kmajor_desc(a), bdesc = tc::make_sw128_kmajor_desc(b);
     long long best = 1ll << 60;
     uint32_t phase = 0;
     for (int r = 0; r < reps; ++r) {
       const long long t0 = clock64();
-      for (int i = 0; i < n_mma; ++i) {
-        const uint32_t k = (uint32_t)(i & 3) * 2;
-        tc::umma_f16(tmem + (uint32_t)((i % n_acc) * N), tc::make_sw128_kmajor_desc(a) + k, tc::make_sw128_kmajor_desc(b) + k, idesc, i >= n_acc);
+      if (tc::elect_one()) {
+        for (int i = 0; i < n_mma; ++i) {
+          const uint64_t k = (uint64_t)((i & 3) * 2);
+          tc::umma_f16(tmem + (uint32_t)((i % n_acc) * N), adesc + k, bdesc + k, idesc, i >= n_acc);
+        }
+        tc::umma_commit(&bar);
       }
-      tc::umma_commit(&bar);
+      __syncwarp();
       tc::mbar_wait(&bar, phase);
       phase ^= 1;
       const long long t1 = clock64();
       if (t1 - t0 < best) best = t1 - t0;
     }
-    out[blockIdx.x] = best;
+    if ((threadIdx.x & 31) == 0) out[blockIdx.x] = best;
   }
   tc::tc_fence_before();
   __syncthreads();

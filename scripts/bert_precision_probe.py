@@ -33,9 +33,10 @@ def logits(state, ids, mask, seg, nh, a_kind, w_kind, att_kind, dt=torch.float32
         q = sp(lin(x, p + "attention.self.query.weight", p + "attention.self.query.bias"))
         k = sp(lin(x, p + "attention.self.key.weight", p + "attention.self.key.bias"))
         v = sp(lin(x, p + "attention.self.value.weight", p + "attention.self.value.bias"))
-        s = rnd(q, att_kind) @ rnd(k, att_kind).transpose(-1, -2) / math.sqrt(dh) + kb
+        ak, bk = att_kind if isinstance(att_kind, tuple) else (att_kind, att_kind)
+        s = rnd(q, ak) @ rnd(k, bk).transpose(-1, -2) / math.sqrt(dh) + kb
         pr = torch.softmax(s, -1)
-        ctx = (rnd(pr, att_kind) @ rnd(v, att_kind)).transpose(1, 2).reshape(N, L, H)
+        ctx = (rnd(pr, ak) @ rnd(v, bk)).transpose(1, 2).reshape(N, L, H)
         y = lin(ctx, p + "attention.output.dense.weight", p + "attention.output.dense.bias")
         x = F.layer_norm(x + y, (H,), g(p + "attention.output.LayerNorm.weight"), g(p + "attention.output.LayerNorm.bias"), eps)
         y = F.gelu(lin(x, p + "intermediate.dense.weight", p + "intermediate.dense.bias"))
@@ -62,6 +63,6 @@ if __name__ == "__main__":
         ref32 = logits(state, ids, mask, seg, nh, "fp32", "fp32", "fp32").numpy()
         gold = g["logits"][:nmax]
         print("shape", ids.shape, "logit scale", np.abs(gold).max(), "fp32 vs golden", rel_err(ref32[:, 1], gold[:, 1], 1e-2), "fp32 vs fp64", rel_err(ref32[:, 1], ref64[:, 1], 1e-2))
-        for a_kind, w_kind, att_kind in [("bf16", "bf16", "bf16"), ("tf32", "tf32", "tf32"), ("fp16", "fp16", "fp16"), ("fp16", "fp32", "fp16"), ("fp16", "fp32", "fp32"), ("fp32", "fp16", "fp32"), ("fp32", "fp32", "fp16"), ("fp16x2", "fp16", "fp16x2"), ("fp16", "fp16x2", "fp16")]:
+        for a_kind, w_kind, att_kind in [("bf16", "bf16", "bf16"), ("tf32", "tf32", "tf32"), ("fp16", "fp16", "fp16"), ("fp16", "fp32", "fp16"), ("fp16", "fp32", "fp32"), ("fp32", "fp16", "fp32"), ("fp32", "fp32", "fp16"), ("fp16x2", "fp16", "fp16x2"), ("fp16", "fp16x2", "fp16"), ("fp16", "fp32", ("fp16", "fp32")), ("fp32", "fp16", ("fp32", "fp16"))]:
             out = logits(state, ids, mask, seg, nh, a_kind, w_kind, att_kind).numpy()
-            print(f"A={a_kind:7s} W={w_kind:7s} att={att_kind:7s}: score err vs golden(floor 1e-2) {rel_err(out[:, 1], gold[:, 1], 1e-2):.2e}   logits (5% floor) {rel_err(out, gold, 0.05 * float(np.abs(gold).max())):.2e}")
+            print(f"A={a_kind:7s} W={w_kind:7s} att={str(att_kind):20s}: score err vs golden(floor 1e-2) {rel_err(out[:, 1], gold[:, 1], 1e-2):.2e}   logits (5% floor) {rel_err(out, gold, 0.05 * float(np.abs(gold).max())):.2e}")

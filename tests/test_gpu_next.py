@@ -102,7 +102,9 @@ def test_convknrm_features_match_reference(shape):
 
 def test_convknrm_chunked_equals_whole(monkeypatch):
     """The rep table is staged chunk by chunk: a 7-pair chunk must give bit-identical scores to one 64-pair chunk."""
-    import capreolus_b200.reranker.ConvKNRM as M
+    import importlib
+
+    M = importlib.import_module("capreolus_b200.reranker.ConvKNRM")  # (the package attribute of that name is the class)
 
     g = load_golden("convknrm_full")
     b = _batch(g)
