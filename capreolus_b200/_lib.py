@@ -62,6 +62,9 @@ SIGNATURES = {
     "capr_convknrm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "capr_convknrm_forward": (c_int, [_i64p, _i64p, c_int, c_int, c_int, _f32p, c_int, c_int, c_int, POINTER(c_void_p), c_int, _f32p, _f32p, c_int,
                                       _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
+    "capr_assemble_pairs": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, _f32p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    _i64p, _i64p, _f32p, c_void_p]),
+    "capr_rank_by_query": (c_int, [_f32p, c_void_p, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
     "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),
     "capr_bert_create": (c_int, [POINTER(BertConfigStruct), POINTER(c_void_p), c_int, c_int, c_void_p, POINTER(c_void_p)]),

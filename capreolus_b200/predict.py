@@ -62,3 +62,174 @@ class PipelinedPredictor:
             scored[i].record(main)
         main.synchronize()
         return self._out_host[: pb.n]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# packed id store -> on-device batch assembly -> scoring -> on-device ranking -> TREC run
+# ---------------------------------------------------------------------------------------------------------------------
+class PackedIdStore:
+    """A tokenised collection (queries or documents) as ONE flat int32 id array + int64 offsets.
+
+    Replaces the per-item Python lists behind ``EmbedText.id2vec`` (``capreolus/extractor/embedtext.py:128-151``:
+    ``qid2toks`` / ``get_doc_tokens`` -> ``_tok2vec``).  Items keep their string ids (``names``); ``idf`` optionally holds
+    one fp32 per token (the ``idfs`` of ``id2vec``)."""
+
+    def __init__(self, names, flat, offsets, idf=None):
+        import numpy as np
+
+        self.names = list(names)
+        self.index = {n: i for i, n in enumerate(self.names)}
+        if len(self.index) != len(self.names):
+            raise ValueError("PackedIdStore: duplicate item ids")
+        self.flat = torch.as_tensor(np.ascontiguousarray(flat, dtype=np.int32))
+        self.offsets = torch.as_tensor(np.ascontiguousarray(offsets, dtype=np.int64))
+        if self.offsets.numel() != len(self.names) + 1 or int(self.offsets[0]) != 0 or int(self.offsets[-1]) != self.flat.numel():
+            raise ValueError("PackedIdStore: offsets must have len(names)+1 entries, start at 0 and end at len(flat)")
+        if self.offsets.numel() > 1 and bool((self.offsets[1:] < self.offsets[:-1]).any()):
+            raise ValueError("PackedIdStore: offsets must be non-decreasing")
+        self.idf = None if idf is None else torch.as_tensor(np.ascontiguousarray(idf, dtype=np.float32))
+        if self.idf is not None and self.idf.numel() != self.flat.numel():
+            raise ValueError("PackedIdStore: idf must be parallel to the flat id array")
+
+    @classmethod
+    def from_lists(cls, items: dict, idf: dict | None = None):
+        """``items``: ``{id: [token ids]}`` (insertion order is kept); ``idf``: ``{id: [fp32 per token]}``."""
+        import numpy as np
+
+        names = list(items)
+        lens = np.fromiter((len(items[n]) for n in names), dtype=np.int64, count=len(names))
+        offsets = np.zeros(len(names) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        flat = np.concatenate([np.asarray(items[n], dtype=np.int32) for n in names]) if names else np.zeros(0, np.int32)
+        idfs = None
+        if idf is not None:
+            idfs = np.concatenate([np.asarray(idf[n], dtype=np.float32) for n in names]) if names else np.zeros(0, np.float32)
+        return cls(names, flat, offsets, idfs)
+
+    def __len__(self):
+        return len(self.names)
+
+    def to(self, device):
+        self.flat, self.offsets = self.flat.to(device), self.offsets.to(device)
+        if self.idf is not None:
+            self.idf = self.idf.to(device)
+        return self
+
+
+class PairAssembler:
+    """``capr_assemble_pairs``: (query index, doc index) vectors -> the padded int64 batch the rerankers consume."""
+
+    def __init__(self, queries: PackedIdStore, docs: PackedIdStore, maxqlen: int, maxdoclen: int, device):
+        self.device = torch.device(device)
+        self.queries, self.docs = queries.to(self.device), docs.to(self.device)
+        self.Q, self.D = int(maxqlen), int(maxdoclen)
+
+    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None) -> dict:
+        from capreolus_b200 import _lib
+
+        _lib.require_cuda(qidx, didx)
+        if qidx.dtype != torch.int32 or didx.dtype != torch.int32:
+            raise ValueError("PairAssembler.assemble: index vectors must be int32")
+        n = qidx.shape[0]
+        if out is None:
+            out = {"query": torch.empty((n, self.Q), dtype=torch.int64, device=self.device),
+                   "posdoc": torch.empty((n, self.D), dtype=torch.int64, device=self.device),
+                   "query_idf": torch.empty((n, self.Q), dtype=torch.float32, device=self.device)}
+        q, d = self.queries, self.docs
+        _lib.check(_lib.lib().capr_assemble_pairs(
+            q.flat.data_ptr(), q.offsets.data_ptr(), len(q), d.flat.data_ptr(), d.offsets.data_ptr(), len(d), _lib.ptr(q.idf),
+            qidx.contiguous().data_ptr(), didx.contiguous().data_ptr(), n, self.Q, self.D, out["query"].data_ptr(), out["posdoc"].data_ptr(),
+            out["query_idf"].data_ptr(), _lib.current_stream(self.device)))
+        return out
+
+
+def rank_by_query(scores: torch.Tensor, seg_off: torch.Tensor, max_segment: int):
+    """``capr_rank_by_query``: (float16-rounded scores ``[N]`` fp32, per-query order ``[N]`` int32); see include/capr_b200.h."""
+    from capreolus_b200 import _lib
+
+    _lib.require_cuda(scores, seg_off)
+    scores = scores.contiguous().float()
+    rounded = torch.empty_like(scores)
+    order = torch.empty(scores.shape[0], dtype=torch.int32, device=scores.device)
+    _lib.check(_lib.lib().capr_rank_by_query(scores.data_ptr(), seg_off.contiguous().data_ptr(), seg_off.shape[0] - 1, int(max_segment),
+                                            rounded.data_ptr(), order.data_ptr(), _lib.current_stream(scores.device)))
+    return rounded, order
+
+
+def write_trec_run(preds: dict, outfn, mode="wt"):
+    """``Searcher.write_trec_run`` (capreolus/searcher/__init__.py:48-58), same file format and ordering."""
+    with open(outfn, mode) as outf:
+        for qid in sorted(preds.keys(), key=lambda k: int(k)):
+            for rank, (docid, score) in enumerate(sorted(preds[qid].items(), key=lambda x: x[1], reverse=True), start=1):
+                print(f"{qid} Q0 {docid} {rank} {score} capreolus", file=outf)
+
+
+class RunPredictor:
+    """``PytorchTrainer.predict`` (capreolus/trainer/pytorch.py:310-353) for a packed collection.
+
+    ``predict(reranker, qid_to_docids, pred_fn)`` scores every (qid, docid) candidate, returns the reference's
+    ``{qid: {docid: float16-rounded score}}`` dict and (optionally) writes the TREC run.  Per chunk only the two int32 index
+    vectors cross PCIe (8 B per pair instead of the 4 352 B of padded int64 ids); rows are assembled, scored, rounded and
+    ranked on the device, and the run file is written from the device-computed order (no Python sort)."""
+
+    def __init__(self, assembler: PairAssembler, chunk: int = 16384):
+        self.assembler, self.chunk = assembler, int(chunk)
+        self.device = assembler.device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    @torch.no_grad()
+    def score_indices(self, reranker, qidx_host: torch.Tensor, didx_host: torch.Tensor) -> torch.Tensor:
+        """Device scores ``[N]`` for pinned host int32 index vectors (H2D of chunk i+1 overlaps scoring of chunk i)."""
+        n = qidx_host.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        scores = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_stream(main)
+            qd = qidx_host.to(self.device, non_blocking=True)
+            dd = didx_host.to(self.device, non_blocking=True)
+        main.wait_stream(self.copy_stream)
+        qd.record_stream(main), dd.record_stream(main)
+        bufs = None
+        for lo in range(0, n, self.chunk):
+            hi = min(n, lo + self.chunk)
+            if bufs is None or bufs["query"].shape[0] != hi - lo:
+                bufs = None
+            bufs = self.assembler.assemble(qd[lo:hi], dd[lo:hi], bufs)
+            scores[lo:hi] = reranker.test(bufs).view(-1)
+        return scores
+
+    @torch.no_grad()
+    def predict(self, reranker, qid_to_docids: dict, pred_fn=None) -> dict:
+        import os
+
+        import numpy as np
+
+        a = self.assembler
+        model = reranker.model.to(self.device)
+        model.eval()
+        qids = list(qid_to_docids)
+        lens = np.fromiter((len(qid_to_docids[q]) for q in qids), dtype=np.int64, count=len(qids))
+        seg = np.zeros(len(qids) + 1, dtype=np.int64)
+        np.cumsum(lens, out=seg[1:])
+        n = int(seg[-1])
+        try:
+            qidx = np.repeat(np.fromiter((a.queries.index[q] for q in qids), dtype=np.int32, count=len(qids)), lens)
+            didx = np.fromiter((a.docs.index[d] for q in qids for d in qid_to_docids[q]), dtype=np.int32, count=n)
+        except KeyError as e:  # the reference raises MissingDocError while predicting (sampler/__init__.py:229-232)
+            raise KeyError(f"got none features for prediction: unknown query or document id {e}") from None
+        scores = self.score_indices(reranker, torch.from_numpy(qidx).pin_memory(), torch.from_numpy(didx).pin_memory())
+        rounded, order = rank_by_query(scores, torch.from_numpy(seg).to(self.device), int(lens.max()) if len(lens) else 0)
+        rounded, order = rounded.cpu().numpy(), order.cpu().numpy()
+        preds = {}
+        for i, q in enumerate(qids):
+            docs, s = qid_to_docids[q], rounded[seg[i]:seg[i + 1]]
+            preds[q] = {d: float(x) for d, x in zip(docs, s)}
+        if pred_fn is not None:
+            os.makedirs(os.path.dirname(os.path.abspath(pred_fn)), exist_ok=True)
+            with open(pred_fn, "wt") as outf:
+                for i in sorted(range(len(qids)), key=lambda j: int(qids[j])):
+                    q, docs, base = qids[i], qid_to_docids[qids[i]], int(seg[i])
+                    for rank in range(int(lens[i])):
+                        pos = int(order[base + rank])
+                        print(f"{q} Q0 {docs[pos]} {rank + 1} {float(rounded[base + pos])} capreolus", file=outf)
+        return preds

@@ -171,6 +171,24 @@ int capr_convknrm_forward(const int64_t* query, const int64_t* doc, int B, int Q
                           const float* w1, const float* b1, int hidden, const float* w2, const float* b2, int flags,
                           float* scores, float* feats_out, void* workspace, size_t workspace_bytes, capr_stream_t stream);
 
+/* ---- predict-loop plumbing ------------------------------------------------
+ * capr_assemble_pairs replaces EmbedText.id2vec / padlist per pair (capreolus/extractor/embedtext.py:128-162,
+ * capreolus/utils/common.py:99-111) as driven by PredSampler.generate_samples (capreolus/sampler/__init__.py:222-233):
+ * the tokenised queries and documents live once on the device as packed id stores (q_store / d_store: flat int32 token ids,
+ * q_off [n_queries+1] / d_off [n_docs+1]: int64 offsets; idf_store: optional fp32 parallel to q_store) and a batch is two
+ * int32 index vectors.  Output rows are what the rerankers consume: query_out [N,Q], doc_out [N,D] int64, truncated to
+ * Q / D tokens and right-padded with 0; idf_out [N,Q] (nullable).  An index outside the store gives an all-pad row. */
+int capr_assemble_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off,
+                        int n_docs, const float* idf_store, const int32_t* qidx, const int32_t* didx, int N, int Q, int D,
+                        int64_t* query_out, int64_t* doc_out, float* idf_out, capr_stream_t stream);
+/* capr_rank_by_query replaces the float16 rounding of PytorchTrainer.predict (capreolus/trainer/pytorch.py:345-348) and the
+ * per-query sort of Searcher.write_trec_run (capreolus/searcher/__init__.py:48-58).  Pairs of one query are contiguous:
+ * seg_off [n_queries+1] int64.  rounded [N] (nullable) = float(float16(score)); order [N]: for query q, order[seg_off[q]+r]
+ * is the position (inside the segment) of the rank-(r+1) document: score descending, ties in input order (Python's stable
+ * sort).  max_segment = the largest segment length (<= 4096). */
+int capr_rank_by_query(const float* scores, const int64_t* seg_off, int n_queries, int max_segment, float* rounded, int32_t* order,
+                       capr_stream_t stream);
+
 /* ---- pairwise losses (tests / training loop) ------------------------------------------------------
  * pair_hinge_loss (capreolus/reranker/common.py:7,101-103): loss[0] = mean(max(0, 1 - (pos - neg))),
  * grad_pos/grad_neg [B] (nullable) = d loss / d score. */

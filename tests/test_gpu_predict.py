@@ -49,3 +49,89 @@ def test_table_is_rebuilt_when_the_embedding_changes():
         s2 = rr.test(b)
     assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-5)
     assert not torch.allclose(s0, s2, rtol=1e-3, atol=1e-3)
+
+
+# ---- on-device batch assembly, ranking, run files ------------------------------------------------
+def _collection(n_q, n_d, Q, D, V, seed):
+    rng = np.random.default_rng(seed)
+    queries = {str(100 + i): rng.integers(1, V, size=rng.integers(0, Q + 5)).tolist() for i in range(n_q)}
+    docs = {f"doc{i}": rng.integers(1, V, size=rng.integers(0, D + 40)).tolist() for i in range(n_d)}
+    idf = {k: rng.random(len(v)).astype(np.float32).tolist() for k, v in queries.items()}
+    return queries, docs, idf
+
+
+def _padlist(x, n, pad=0):  # capreolus/utils/common.py:99-111
+    x = list(x)[:n]
+    return x + [pad] * (n - len(x))
+
+
+def test_assemble_pairs_equals_padlist():
+    from capreolus_b200.predict import PackedIdStore, PairAssembler
+
+    Q, D, V = 8, 50, 1000
+    queries, docs, idf = _collection(7, 40, Q, D, V, seed=1)
+    asm = PairAssembler(PackedIdStore.from_lists(queries, idf), PackedIdStore.from_lists(docs), Q, D, DEV)
+    rng = np.random.default_rng(2)
+    qi = rng.integers(0, 7, size=333).astype(np.int32)
+    di = rng.integers(0, 40, size=333).astype(np.int32)
+    out = asm.assemble(torch.from_numpy(qi).to(DEV), torch.from_numpy(di).to(DEV))
+    qn, dn = list(queries), list(docs)
+    want_q = np.array([_padlist(queries[qn[i]], Q) for i in qi], dtype=np.int64)
+    want_d = np.array([_padlist(docs[dn[i]], D) for i in di], dtype=np.int64)
+    want_idf = np.array([_padlist(idf[qn[i]], Q, 0.0) for i in qi], dtype=np.float32)
+    assert out["query"].dtype == torch.int64 and np.array_equal(out["query"].cpu().numpy(), want_q)
+    assert np.array_equal(out["posdoc"].cpu().numpy(), want_d)
+    assert np.array_equal(out["query_idf"].cpu().numpy(), want_idf)
+    # out-of-range indices give all-pad rows; an empty batch is a no-op
+    bad = asm.assemble(torch.tensor([-1, 99], dtype=torch.int32, device=DEV), torch.tensor([400, -5], dtype=torch.int32, device=DEV))
+    assert int(bad["query"].abs().sum()) == 0 and int(bad["posdoc"].abs().sum()) == 0
+    assert asm.assemble(torch.zeros(0, dtype=torch.int32, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV))["query"].shape == (0, Q)
+
+
+@pytest.mark.parametrize("sizes", [[1, 5, 128, 0, 77], [1000, 3, 1024], [4096, 1500, 2]])
+def test_rank_by_query_equals_python_stable_sort(sizes):
+    from capreolus_b200.predict import rank_by_query
+
+    rng = np.random.default_rng(sum(sizes))
+    seg = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    scores = (rng.standard_normal(int(seg[-1])) * 3).astype(np.float32)
+    scores[rng.integers(0, scores.size, size=scores.size // 3)] = 0.5  # plenty of ties
+    rounded, order = rank_by_query(torch.from_numpy(scores).to(DEV), torch.from_numpy(seg).to(DEV), max(sizes))
+    rounded, order = rounded.cpu().numpy(), order.cpu().numpy()
+    want_r = scores.astype(np.float16).astype(np.float32)  # trainer/pytorch.py:347
+    assert np.array_equal(rounded, want_r)
+    for i in range(len(sizes)):
+        s = want_r[seg[i]:seg[i + 1]]
+        want = [j for j, _ in sorted(enumerate(s.tolist()), key=lambda x: x[1], reverse=True)]  # searcher/__init__.py:54
+        assert order[seg[i]:seg[i + 1]].tolist() == want
+
+
+def test_run_predictor_matches_reference_predict_loop(tmp_path):
+    """RunPredictor.predict == the reference loop: id2vec rows -> reranker.test -> float16 -> {qid: {docid: score}} -> write_trec_run."""
+    from capreolus_b200 import reranker as R, synthetic
+    from capreolus_b200.predict import PackedIdStore, PairAssembler, RunPredictor, write_trec_run
+
+    Q, D, V, E = 8, 50, 1000, 50
+    queries, docs, idf = _collection(9, 120, Q, D, V, seed=5)
+    rr = R.DRMM(provide={"extractor": Extractor(synthetic.embedding_table(V, E, seed=0), Q, D)})
+    rr.build_model().to(DEV).eval()
+    rng = np.random.default_rng(6)
+    dn = list(docs)
+    cands = {q: [dn[j] for j in rng.choice(len(dn), size=rng.integers(1, 60), replace=False)] for q in queries}
+    asm = PairAssembler(PackedIdStore.from_lists(queries, idf), PackedIdStore.from_lists(docs), Q, D, DEV)
+    preds = RunPredictor(asm, chunk=100).predict(rr, cands, tmp_path / "out" / "run.txt")
+    # the reference way: one padded row per (qid, docid), scored in one batch
+    rows = [(q, d) for q in cands for d in cands[q]]
+    batch = {"query": torch.tensor([_padlist(queries[q], Q) for q, _ in rows], device=DEV),
+             "posdoc": torch.tensor([_padlist(docs[d], D) for _, d in rows], device=DEV),
+             "query_idf": torch.tensor([_padlist(idf[q], Q, 0.0) for q, _ in rows], dtype=torch.float32, device=DEV)}
+    with torch.no_grad():
+        scores = rr.test(batch).view(-1).cpu().numpy()
+    want = {}
+    for (q, d), s in zip(rows, scores):
+        want.setdefault(q, {})[d] = s.astype(np.float16).item()
+    assert preds == want
+    write_trec_run(want, tmp_path / "ref.txt")
+    assert (tmp_path / "out" / "run.txt").read_text() == (tmp_path / "ref.txt").read_text()
+    with pytest.raises(KeyError, match="none features"):
+        RunPredictor(asm).predict(rr, {"100": ["nosuchdoc"]})

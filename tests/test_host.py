@@ -65,6 +65,8 @@ def test_cpu_tensors_are_rejected_not_silently_scored():
     ("KNRM", "knrm_small", ["default", "twofc", "tanh"]),
     ("DRMM", "drmm_small", ["default", "nh", "ch_tv"]),
     ("PACRR", "pacrr_small", ["default", "noidf_tanh", "wide"]),
+    ("DRMMTKS", "drmmtks_small", ["default", "k3", "k20"]),
+    ("ConvKNRM", "convknrm_small", ["default", "nocross_twofc", "uni_tanh"]),
 ])
 def test_state_dict_keys_and_shapes_match_the_reference(cls, golden, variants):
     cfgs = {
@@ -72,6 +74,9 @@ def test_state_dict_keys_and_shapes_match_the_reference(cls, golden, variants):
         "DRMM": {"default": {}, "nh": {"histType": "NH"}, "ch_tv": {"nbins": 11, "nodes": 7, "histType": "CH", "gateType": "TV"}},
         "PACRR": {"default": {}, "noidf_tanh": {"idf": False, "nonlinearity": "tanh"},
                   "wide": {"mingram": 2, "nfilters": 16, "kmax": 3, "combine": 24, "nonlinearity": "none"}},
+        "DRMMTKS": {"default": {}, "k3": {"topk": 3}, "k20": {"topk": 20, "freezeemb": False}},
+        "ConvKNRM": {"default": {}, "nocross_twofc": {"maxngram": 2, "crossmatch": False, "filters": 48, "singlefc": False},
+                     "uni_tanh": {"gradkernels": False, "maxngram": 1, "scoretanh": True}},
     }[cls]
     g = load_golden(golden)
     B, Q, D, V, E = (int(x) for x in g["shape"])
@@ -80,7 +85,7 @@ def test_state_dict_keys_and_shapes_match_the_reference(cls, golden, variants):
         model = getattr(R, cls)(cfgs[variant], provide={"extractor": Extractor(V, E, Q, D, seed=int(g["table_seed"]))}).build_model()
         ours = model.state_dict()
         assert set(ref_state) <= set(ours), set(ref_state) - set(ours)
-        assert set(ours) - set(ref_state) <= {"embedding.weight", "simmat.embedding.weight"}
+        assert set(ours) - set(ref_state) <= {"embedding.weight", "simmat.embedding.weight", "embeddings.weight"}
         for k, v in ref_state.items():
             assert tuple(ours[k].shape) == tuple(v.shape), k
         model.load_state_dict(ref_state, strict=False)
@@ -190,3 +195,32 @@ def test_sharded_scoring_with_gloo_world_size_2(n):
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(ok and shape == (n,) for _, ok, shape in results), results
+
+
+# ---- packed id store + TREC run writer (host logic) -------------------------------------------
+def test_packed_id_store_layout_and_validation():
+    from capreolus_b200.predict import PackedIdStore
+
+    st = PackedIdStore.from_lists({"d1": [5, 6, 7], "d2": [], "d3": [9]}, idf={"d1": [0.5, 1.0, 1.5], "d2": [], "d3": [2.0]})
+    assert st.names == ["d1", "d2", "d3"] and st.index["d3"] == 2 and len(st) == 3
+    assert st.flat.dtype == torch.int32 and st.flat.tolist() == [5, 6, 7, 9]
+    assert st.offsets.dtype == torch.int64 and st.offsets.tolist() == [0, 3, 3, 4]
+    assert st.idf.tolist() == [0.5, 1.0, 1.5, 2.0]
+    with pytest.raises(ValueError, match="duplicate"):
+        PackedIdStore(["a", "a"], [1, 2], [0, 1, 2])
+    with pytest.raises(ValueError, match="offsets"):
+        PackedIdStore(["a", "b"], [1, 2], [0, 1])
+    with pytest.raises(ValueError, match="non-decreasing"):
+        PackedIdStore(["a", "b"], [1, 2], [0, 3, 2])
+    with pytest.raises(ValueError, match="idf"):
+        PackedIdStore(["a"], [1, 2], [0, 2], idf=[1.0])
+
+
+def test_write_trec_run_matches_the_reference_format(tmp_path):
+    """capreolus/searcher/__init__.py:48-58: qids in int order, docs by score descending (stable), 'qid Q0 docid rank score capreolus'."""
+    from capreolus_b200.predict import write_trec_run
+
+    preds = {"10": {"a": 0.5, "b": 2.0, "c": 0.5}, "9": {"x": -1.25}}
+    fn = tmp_path / "run.txt"
+    write_trec_run(preds, fn)
+    assert fn.read_text().splitlines() == ["9 Q0 x 1 -1.25 capreolus", "10 Q0 b 1 2.0 capreolus", "10 Q0 a 2 0.5 capreolus", "10 Q0 c 3 0.5 capreolus"]
