@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "bert_attn.cuh"
+#include "bert_attn2.cuh"
 #include "tmap.cuh"
 
 namespace capr {
@@ -334,6 +335,7 @@ struct Model {
   std::vector<void*> owned;
   int sms = 0;
   bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
+  bool attention_v1 = false;    // CAPR_BERT_ATTENTION=v1: the first tensor-core attention (128 queries per CTA), for A/B tests
 };
 
 static int dev_alloc(Model* m, void** p, size_t bytes) {
@@ -453,6 +455,7 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
   {
     const char* e = getenv("CAPR_BERT_ATTENTION");
     m->ffma_attention = e && e[0] == 'f';
+    m->attention_v1 = e && e[0] == 'v' && e[1] == '1';
   }
   const size_t H = cfg->hidden, I = cfg->intermediate;
   int rc = CAPR_OK;
@@ -571,14 +574,18 @@ int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, co
       CAPR_CHECK_CUDA(cudaMemsetAsync(qkv_lo + T * 3 * H, 0, (Tp - T) * 3 * H * 2, st));
     }
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
+    CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
   }
+  const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
+  const int att_tc2_grid = n_seq * heads * ((L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ));
   const AttnArgs at{L, H, heads, n_seq, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
   const int att_tc_grid = n_seq * heads * ((L + AT_BQ - 1) / AT_BQ);
   for (int l = 0; l < m->cfg.layers; ++l) {
     const Layer& ly = m->layers[l];
     if (tc_attention) {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_SPLIT, nullptr, nullptr, qkv_hi, qkv_lo, st))) return rc;
-      attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
+      if (m->attention_v1) attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
+      else attention_tc2_kernel<<<att_tc2_grid, A2_THREADS, A2_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
       CAPR_CHECK_CUDA(cudaGetLastError());
     } else {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;
