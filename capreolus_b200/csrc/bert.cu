@@ -517,15 +517,19 @@ size_t capr_bert_workspace_bytes(capr_bert_t h, int n_seq, int L) {
   return carve(m->cfg, (size_t)n_seq * L, nullptr, nullptr);
 }
 
-int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, float* logits,
-                      void* workspace, size_t workspace_bytes, capr_stream_t stream) {
-  const char* fn = "capr_bert_forward";
+// Shared body of capr_bert_forward / capr_bert_forward_hidden.  hidden_layers[i] in [0, layers]: 0 = embedding output,
+// l = output of encoder layer l (HF `hidden_states[l]`); the fp32 activations are copied to hidden_out[i] ([T,H] each).
+static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, float* logits,
+                    const int* hidden_layers, int n_hidden, float* hidden_out, void* workspace, size_t workspace_bytes, capr_stream_t stream) {
   Model* m = (Model*)h;
   CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
-  CAPR_REQUIRE(n_seq >= 0 && L > 0, CAPR_ERR_BAD_SHAPE, "%s: n_seq=%d L=%d", fn, n_seq, L);
+  CAPR_REQUIRE(n_seq >= 0 && L > 0 && n_hidden >= 0, CAPR_ERR_BAD_SHAPE, "%s: n_seq=%d L=%d", fn, n_seq, L);
   if (n_seq == 0) return CAPR_OK;
   CAPR_REQUIRE(L <= m->cfg.max_pos, CAPR_ERR_BAD_SHAPE, "%s: sequence length %d exceeds max_position_embeddings %d", fn, L, m->cfg.max_pos);
-  CAPR_REQUIRE(ids && mask && seg && logits && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(ids && mask && seg && (logits || n_hidden > 0) && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(n_hidden == 0 || (hidden_layers && hidden_out), CAPR_ERR_BAD_POINTER, "%s: hidden states requested without buffers", fn);
+  for (int i = 0; i < n_hidden; ++i)
+    CAPR_REQUIRE(hidden_layers[i] >= 0 && hidden_layers[i] <= m->cfg.layers, CAPR_ERR_BAD_SHAPE, "%s: hidden layer %d not in [0, %d]", fn, hidden_layers[i], m->cfg.layers);
   CAPR_REQUIRE(((uintptr_t)workspace & 255) == 0, CAPR_ERR_BAD_POINTER, "%s: workspace must be 256-byte aligned", fn);
   const size_t T = (size_t)n_seq * L;
   CAPR_REQUIRE(T < (size_t)1 << 31, CAPR_ERR_BAD_SHAPE, "%s: too many tokens in one call (%zu); split the batch", fn, T);
@@ -557,6 +561,13 @@ int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, co
                                               m->cfg.type_vocab, m->word, m->pos, m->type, m->emb_g, m->emb_b, m->cfg.ln_eps, ws.x, ws.x_hi,
                                               ws.x_lo);
   CAPR_CHECK_CUDA(cudaGetLastError());
+  auto emit_hidden = [&](int layer_index) -> int {
+    for (int i = 0; i < n_hidden; ++i)
+      if (hidden_layers[i] == layer_index)
+        CAPR_CHECK_CUDA(cudaMemcpyAsync(hidden_out + (size_t)i * T * H, ws.x, T * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return CAPR_OK;
+  };
+  if ((rc = emit_hidden(0))) return rc;
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
   const int att_grid = n_seq * heads * ((L + ATT_BQ - 1) / ATT_BQ);
   // tensor-core attention: head dim 64, L <= 512; Q/K/V then live as bf16 (hi, lo) planes aliased onto the fp32 qkv buffer
@@ -601,10 +612,24 @@ int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, co
     if ((rc = gemm(m, f_hi, f_lo, ly.ffn2, Ti, EPI_BIAS_RESID_F32, ws.x, ws.y, nullptr, nullptr, st))) return rc;
     ln_kernel<<<row_blocks, 256, 0, st>>>(ws.y, Ti, H, ly.ln2_g, ly.ln2_b, m->cfg.ln_eps, ws.x, ws.x_hi, ws.x_lo);
     CAPR_CHECK_CUDA(cudaGetLastError());
+    if ((rc = emit_hidden(l + 1))) return rc;
   }
-  pooler_classifier_kernel<<<n_seq, 256, 2 * H * sizeof(float), st>>>(ws.x, L, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, m->cfg.n_labels, logits);
-  CAPR_CHECK_CUDA(cudaGetLastError());
+  if (logits) {
+    pooler_classifier_kernel<<<n_seq, 256, 2 * H * sizeof(float), st>>>(ws.x, L, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, m->cfg.n_labels, logits);
+    CAPR_CHECK_CUDA(cudaGetLastError());
+  }
   return CAPR_OK;
+}
+
+int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, float* logits,
+                      void* workspace, size_t workspace_bytes, capr_stream_t stream) {
+  CAPR_REQUIRE(logits || n_seq == 0, CAPR_ERR_BAD_POINTER, "capr_bert_forward: null pointer");
+  return bert_run("capr_bert_forward", h, ids, mask, seg, n_seq, L, logits, nullptr, 0, nullptr, workspace, workspace_bytes, stream);
+}
+
+int capr_bert_forward_hidden(capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, const int* hidden_layers,
+                             int n_hidden, float* hidden_out, float* logits, void* workspace, size_t workspace_bytes, capr_stream_t stream) {
+  return bert_run("capr_bert_forward_hidden", h, ids, mask, seg, n_seq, L, logits, hidden_layers, n_hidden, hidden_out, workspace, workspace_bytes, stream);
 }
 
 // Debug / test entry: C = A . W^T + bias through the same tcgen05 kernel (A [M,K], W [N,K], fp32 device buffers).

@@ -57,5 +57,6 @@ from capreolus_b200.reranker.PACRR import PACRR, PACRR_class  # noqa: E402,F401
 from capreolus_b200.reranker.ptBERTMaxP import PTBERTMaxP, PTBERTMaxP_Class  # noqa: E402,F401
 from capreolus_b200.reranker.DRMMTKS import DRMMTKS, DRMMTKS_class  # noqa: E402,F401
 from capreolus_b200.reranker.ConvKNRM import ConvKNRM, ConvKNRM_class  # noqa: E402,F401
+from capreolus_b200.reranker.CEDRKNRM import CEDRKNRM, CEDRKNRM_Class  # noqa: E402,F401
 
-__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class", "DRMMTKS", "DRMMTKS_class", "ConvKNRM", "ConvKNRM_class"]
+__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class", "DRMMTKS", "DRMMTKS_class", "ConvKNRM", "ConvKNRM_class", "CEDRKNRM", "CEDRKNRM_Class"]

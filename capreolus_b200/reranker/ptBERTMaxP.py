@@ -25,13 +25,15 @@ _LAYER_KEYS = [
 ]
 
 
-def bert_weight_keys(n_layers: int) -> list[str]:
-    """state_dict keys of a HF BertForSequenceClassification in the order ``capr_bert_create`` expects them."""
-    keys = ["bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
-            "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias"]
+def bert_weight_keys(n_layers: int, prefix: str = "bert.", classifier: bool = True) -> list[str]:
+    """state_dict keys of a HF BertForSequenceClassification (``prefix='bert.'``) or BertModel (``prefix=''``,
+    ``classifier=False``) in the order ``capr_bert_create`` expects them."""
+    keys = [prefix + "embeddings.word_embeddings.weight", prefix + "embeddings.position_embeddings.weight",
+            prefix + "embeddings.token_type_embeddings.weight", prefix + "embeddings.LayerNorm.weight", prefix + "embeddings.LayerNorm.bias"]
     for i in range(n_layers):
-        keys += [f"bert.encoder.layer.{i}.{k}" for k in _LAYER_KEYS]
-    return keys + ["bert.pooler.dense.weight", "bert.pooler.dense.bias", "classifier.weight", "classifier.bias"]
+        keys += [f"{prefix}encoder.layer.{i}.{k}" for k in _LAYER_KEYS]
+    keys += [prefix + "pooler.dense.weight", prefix + "pooler.dense.bias"]
+    return keys + (["classifier.weight", "classifier.bias"] if classifier else [])
 
 
 class BertEngine:
@@ -48,11 +50,16 @@ class BertEngine:
         if getattr(cfg, "position_embedding_type", "absolute") != "absolute":
             raise ValueError("capreolus_b200 ptBERTMaxP: only absolute position embeddings are implemented")
         state = hf_model.state_dict()
-        keys = bert_weight_keys(cfg.num_hidden_layers)
+        headless = "classifier.weight" not in state  # a bare BertModel (CEDR-KNRM): no classification head
+        keys = bert_weight_keys(cfg.num_hidden_layers, "" if headless else "bert.", classifier=not headless)
         tensors = [state[k].detach().float().contiguous() for k in keys]
         _lib.require_cuda(*tensors)
         self.device = tensors[0].device
-        self.n_labels = state["classifier.weight"].shape[0]
+        if headless:  # capr_bert_create wants a classifier: hand it zeros (logits are never requested from such an engine)
+            tensors += [torch.zeros((2, cfg.hidden_size), device=self.device), torch.zeros(2, device=self.device)]
+        self.headless = headless
+        self.hidden_size, self.n_layers = cfg.hidden_size, cfg.num_hidden_layers
+        self.n_labels = tensors[-2].shape[0]
         self.cfg = _lib.BertConfigStruct(cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size,
                                          cfg.vocab_size, cfg.max_position_embeddings, cfg.type_vocab_size, self.n_labels,
                                          float(cfg.layer_norm_eps))
@@ -74,6 +81,27 @@ class BertEngine:
                 self.handle = None
         except Exception:
             pass
+
+    def _ws(self, n, L, device):
+        need = _lib.lib().capr_bert_workspace_bytes(self.handle, n, L)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._workspace
+
+    def hidden_states(self, ids, mask, seg, layers) -> torch.Tensor:
+        """``[N,L]`` int64 x3 -> fp32 ``[len(layers), N*L, H]``: HF ``hidden_states[l]`` for l in ``layers`` (0 = embedding
+        output).  One call: the caller chunks N (``capr_bert_forward_hidden``)."""
+        _lib.require_cuda(ids, mask, seg)
+        ids, mask, seg = (t.long().contiguous() for t in (ids, mask, seg))
+        N, L = ids.shape
+        layers = [int(l) for l in layers]
+        out = torch.empty((len(layers), N * L, self.hidden_size), dtype=torch.float32, device=ids.device)
+        with torch.cuda.device(ids.device):
+            ws = self._ws(N, L, ids.device)
+            arr = (ctypes.c_int * len(layers))(*layers)
+            _lib.check(_lib.lib().capr_bert_forward_hidden(self.handle, ids.data_ptr(), mask.data_ptr(), seg.data_ptr(), N, L, arr, len(layers),
+                                                           out.data_ptr(), None, ws.data_ptr(), ws.numel(), _lib.current_stream(ids.device)))
+        return out
 
     def logits(self, ids, mask, seg) -> torch.Tensor:
         """``[N,L]`` int64 x3 -> classifier logits ``[N,n_labels]`` fp32."""

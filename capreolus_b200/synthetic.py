@@ -129,3 +129,27 @@ def bert_batch(n: int, seqlen: int = 512, qlen: int = 32, vocab: int = BERT_VOCA
             mask[b, p, : len(toks)] = 1
             seg[b, p, qlen + 2:] = 1  # stays 1 through the padding (tests/test_extractor.py:708-713)
     return {"pos_bert_input": ids, "pos_mask": mask, "pos_seg": seg}
+
+
+def cedr_batch(n: int, numpassages: int, seqlen: int, maxqlen: int, vocab: int = BERT_VOCAB, seed: int = 6) -> dict:
+    """Passage inputs in the ``pooledbertpassage`` layout CEDR-KNRM consumes (``capreolus/extractor/bertpassage.py:268-284``):
+    ``[CLS] q [SEP] passage [SEP] [PAD]...`` with the SAME query in every passage of a document, ragged query lengths
+    (1..maxqlen), ragged passages and some completely empty trailing passages; arrays are ``[n, P, L] int64``."""
+    rng = np.random.default_rng(seed)
+    ids = np.zeros((n, numpassages, seqlen), dtype=np.int64)
+    mask = np.zeros_like(ids)
+    seg = np.zeros_like(ids)
+    lo = min(1000, vocab // 2)
+    for b in range(n):
+        ql = maxqlen if b == 0 else int(rng.integers(1, maxqlen + 1))
+        q = list(rng.integers(lo, vocab, size=ql))
+        for p in range(numpassages):
+            max_d = seqlen - ql - 3
+            nd = max_d if (b + p) % 3 == 0 else int(rng.integers(1, max_d + 1))
+            if numpassages > 1 and p == numpassages - 1 and b % 2 == 1:
+                nd = 0  # an empty trailing passage: "[CLS] q [SEP] [SEP]"
+            toks = [CLS] + q + [SEP] + list(rng.integers(lo, vocab, size=nd)) + [SEP]
+            ids[b, p, : len(toks)] = toks
+            mask[b, p, : len(toks)] = 1
+            seg[b, p, ql + 2:] = 1
+    return {"pos_bert_input": ids, "pos_mask": mask, "pos_seg": seg}

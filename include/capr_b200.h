@@ -228,6 +228,31 @@ size_t capr_bert_workspace_bytes(capr_bert_t handle, int n_seq, int L);
  * logits [n_seq, n_labels] fp32 = the classifier output; the passage score is logits[:, 1]. */
 int capr_bert_forward(capr_bert_t handle, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L,
                       float* logits, void* workspace, size_t workspace_bytes, capr_stream_t stream);
+/* Same encoder, additionally copying fp32 hidden states out (HF `output_hidden_states=True`, as CEDRKNRM.py:19-38 asks for):
+ * hidden_layers [n_hidden] (HOST ints in [0, layers]: 0 = embedding output, l = output of encoder layer l) ->
+ * hidden_out [n_hidden, n_seq*L, H] fp32.  logits may be NULL (encoder without a classification head). */
+int capr_bert_forward_hidden(capr_bert_t handle, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L,
+                             const int* hidden_layers, int n_hidden, float* hidden_out, float* logits, void* workspace,
+                             size_t workspace_bytes, capr_stream_t stream);
+
+/* ---- CEDR-KNRM head ------------------------------------------------------------------
+ * CEDRKNRM_Class.masked_simmats / knrm / forward (capreolus/reranker/CEDRKNRM.py:85-171) on the hidden states
+ * capr_bert_forward_hidden produced for n_seq = B*P passages ([CLS] q [SEP] doc [SEP] pad; P passages per document):
+ *   hidden [n_layers, B*P*L, H]   the layers listed in `simmat_layers` (n_layers may be 0: cls feature only)
+ *   last_hidden [B*P*L, H]        hidden_states[-1] (its [CLS] rows give the cls feature; NULL when cls_mode == 0)
+ *   query rows = positions 1..maxqlen+1 masked by mask*(seg==0); doc columns = positions 1..L-1 masked by mask*(seg==1);
+ *   cosine = a.b / ((|a|+1e-9)(|b|+1e-9)); K kernels (mu, sigma [K]) summed over the unmasked doc tokens of all P passages,
+ *   log(clamp(., 1e-10)) * 0.01, summed over the maxqlen+1 query rows -> K features per layer.
+ *   cls_mode: 0 none, 1 avg, 2 max over the passages.   feats [B, F], F = capr_cedrknrm_feature_dim (cls first).
+ *   combine: w1 [combine_hidden or 1, F], b1; w2 [1, combine_hidden], b2 (combine_hidden == 0: single Linear(F,1)).
+ *   scores [B] (nullable).  workspace: capr_cedrknrm_workspace_bytes(B*P, maxqlen, n_layers, K).
+ * Limits: maxqlen < 64, K <= 32, H <= 1024 and a multiple of 4. */
+int capr_cedrknrm_feature_dim(int H, int n_layers, int K, int cls_mode);
+size_t capr_cedrknrm_workspace_bytes(int n_seq, int maxqlen, int n_layers, int K);
+int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidden, const int64_t* mask, const int64_t* seg, int B,
+                       int P, int L, int H, int maxqlen, const float* mu, const float* sigma, int K, int cls_mode, const float* w1,
+                       const float* b1, int combine_hidden, const float* w2, const float* b2, float* feats, float* scores,
+                       void* workspace, size_t workspace_bytes, capr_stream_t stream);
 /* Test hook: C[M,N] = A[M,K] . W[N,K]^T + bias through the encoder's tcgen05 GEMM kernel (synchronises the stream). */
 int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c,
                    capr_stream_t stream);

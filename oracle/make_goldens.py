@@ -298,6 +298,58 @@ def make_bert():
         print("bert", name, out["logits"][:3].tolist())
 
 
+CEDR_CONFIGS = {
+    # name: (BertConfig kwargs, N docs, P passages, L, maxqlen, weight seed, input seed, reranker config)
+    "tiny": (dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, vocab_size=1000, max_position_embeddings=64),
+             6, 3, 48, 6, 0, 13, dict(simmat_layers=[0, 1, 2], combine_hidden=16, cls="avg")),
+    "mid": (dict(hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=1024, vocab_size=5000, max_position_embeddings=512,
+                 initializer_range=0.08), 4, 2, 200, 16, 0, 15, dict(simmat_layers=[1, 3], combine_hidden=0, cls="max")),
+    "base": (dict(), 2, 2, 512, 32, 0, 17, dict(simmat_layers=list(range(13)), combine_hidden=128, cls="avg")),  # CEDRKNRM.py defaults (combine_hidden 128 keeps the fixture small), BERT-base
+}
+
+
+def make_cedrknrm():
+    """the reference CEDRKNRM wrapper driving a seeded random-init HF BertModel."""
+    mod = refshim.load_cedrknrm()
+    for name, (cfg, N, P, L, maxqlen, wseed, iseed, rcfg) in CEDR_CONFIGS.items():
+        import transformers
+
+        vocab = transformers.BertConfig(**cfg).vocab_size
+        batch = synthetic.cedr_batch(N, P, L, maxqlen, vocab=vocab, seed=iseed)
+        tb = _t(batch)
+        out = {k: v.astype(np.int32) for k, v in batch.items()}
+        out.update(reference_commit=np.array(refshim.REFERENCE_COMMIT), weight_seed=np.array(wseed), input_seed=np.array(iseed),
+                   shape=np.array([N, P, L, maxqlen]))
+        ext = refshim.FakeExtractor(None, numpassages=P, maxseqlen=L, maxqlen=maxqlen)
+        variants = {"default": rcfg, "nocls": {**rcfg, "cls": None}}
+        if name == "tiny":
+            variants["clsonly"] = {**rcfg, "simmat_layers": [-1]}
+        for variant, vcfg in variants.items():
+            full = dict(pretrained="bert-base-uncased", mus=[-0.9, -0.7, -0.5, -0.3, -0.1, 0.1, 0.3, 0.5, 0.7, 0.9], sigma=0.1, gradkernels=True,
+                        hidden_dropout_prob=0.1, **vcfg)
+            with refshim.patched_bertmodel_from_pretrained(cfg, seed=wseed):
+                torch.manual_seed(600)
+                rr = mod.CEDRKNRM(full, provide={"extractor": ext})
+                model = rr.build_model().eval()
+            with torch.no_grad():
+                # the knrm features are 0.01*log sums (|x| ~ 1) against 768 cls dims: give them weight in the parity check
+                model.combine[0].weight[:, -model.kernels.count() * len([l for l in vcfg["simmat_layers"] if l >= 0]):].mul_(5.0) if -1 not in vcfg["simmat_layers"] else None
+                scores = rr.test(tb)
+                out[f"{variant}/scores"] = scores.numpy()
+                if variant == "default":
+                    grabbed = []
+                    h = model.combine[0].register_forward_hook(lambda m, i, o: grabbed.append(i[0].detach().clone()))
+                    rr.test(tb)
+                    h.remove()
+                    out["feats"] = grabbed[0].numpy()
+                    out["weight_checksum"] = bert_weight_checksum(model.bert)
+                    out["config_json"] = np.array(model.bert.config.to_json_string())
+            out.update({f"{variant}/{k}": v for k, v in _state_np(model, skip=("bert.", "one", "zero")).items()})
+            out[f"{variant}/config_json"] = np.array(__import__("json").dumps(vcfg))
+        np.savez_compressed(GOLDEN / f"cedrknrm_{name}.npz", **out)
+        print("cedrknrm", name, out["default/scores"][:3].tolist())
+
+
 TRAIN = dict(batch=32, itersize=512, niters=2, lr=1e-3, seed=4)
 
 
@@ -368,7 +420,7 @@ def make_losses():
                         hinge=ref.common.pair_hinge_loss([tp, tn]).numpy(), softmax=ref.common.pair_softmax_loss([tp, tn]).numpy())
 
 
-ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "drmmtks": make_drmmtks, "convknrm": make_convknrm, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
+ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "drmmtks": make_drmmtks, "convknrm": make_convknrm, "cedrknrm": make_cedrknrm, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)

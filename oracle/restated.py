@@ -296,23 +296,25 @@ def pair_softmax_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
 # BERT math (modeling_bert.py: embeddings -> 12 x {self-attention, output LN, erf-GELU FFN, output LN}
 # -> pooler tanh -> classifier).  This is a restatement of that published algorithm; it is pinned
 # against the installed HF implementation in tests/test_oracle.py.
-def bert_logits(state: dict, ids, mask, seg, num_heads: int, eps: float = 1e-12) -> torch.Tensor:
-    """``BertForSequenceClassification(ids, attention_mask=mask, token_type_ids=seg).logits`` in eval mode.
+def bert_hidden_states(state: dict, ids, mask, seg, num_heads: int, eps: float = 1e-12, prefix: str = "bert.") -> list:
+    """HF BertModel ``hidden_states`` (embedding output + one entry per encoder layer), eval mode.
 
-    ``state`` uses HF key names (``bert.embeddings.word_embeddings.weight`` ...); ids/mask/seg ``[N,L]`` int64."""
+    ``state`` uses HF key names with ``prefix`` (``bert.`` for BertForSequenceClassification, empty for BertModel)."""
     N, L = ids.shape
-    g = lambda k: state[k]
-    x = F.embedding(ids, g("bert.embeddings.word_embeddings.weight"))
-    x = x + F.embedding(seg, g("bert.embeddings.token_type_embeddings.weight"))
-    x = x + g("bert.embeddings.position_embeddings.weight")[:L][None]
+    g = lambda k: state[prefix + k]
+    x = F.embedding(ids, g("embeddings.word_embeddings.weight"))
+    x = x + F.embedding(seg, g("embeddings.token_type_embeddings.weight"))
+    x = x + g("embeddings.position_embeddings.weight")[:L][None]
     H = x.shape[-1]
-    x = F.layer_norm(x, (H,), g("bert.embeddings.LayerNorm.weight"), g("bert.embeddings.LayerNorm.bias"), eps)
+    x = F.layer_norm(x, (H,), g("embeddings.LayerNorm.weight"), g("embeddings.LayerNorm.bias"), eps)
+    hidden = [x]
     dh = H // num_heads
     key_bias = torch.zeros(N, 1, 1, L, dtype=x.dtype)
     key_bias.masked_fill_(mask[:, None, None, :] == 0, torch.finfo(x.dtype).min)
-    n_layers = 1 + max(int(k.split(".")[3]) for k in state if k.startswith("bert.encoder.layer."))
+    lp = prefix + "encoder.layer."
+    n_layers = 1 + max(int(k[len(lp):].split(".")[0]) for k in state if k.startswith(lp))
     for i in range(n_layers):
-        p = f"bert.encoder.layer.{i}."
+        p = f"encoder.layer.{i}."
         split = lambda t: t.reshape(N, L, num_heads, dh).transpose(1, 2)
         qh = split(F.linear(x, g(p + "attention.self.query.weight"), g(p + "attention.self.query.bias")))
         kh = split(F.linear(x, g(p + "attention.self.key.weight"), g(p + "attention.self.key.bias")))
@@ -324,8 +326,73 @@ def bert_logits(state: dict, ids, mask, seg, num_heads: int, eps: float = 1e-12)
         y = F.gelu(F.linear(x, g(p + "intermediate.dense.weight"), g(p + "intermediate.dense.bias")))  # erf GELU
         y = F.linear(y, g(p + "output.dense.weight"), g(p + "output.dense.bias"))
         x = F.layer_norm(x + y, (H,), g(p + "output.LayerNorm.weight"), g(p + "output.LayerNorm.bias"), eps)
-    pooled = torch.tanh(F.linear(x[:, 0], g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias")))
-    return F.linear(pooled, g("classifier.weight"), g("classifier.bias"))
+        hidden.append(x)
+    return hidden
+
+
+def bert_logits(state: dict, ids, mask, seg, num_heads: int, eps: float = 1e-12) -> torch.Tensor:
+    """``BertForSequenceClassification(ids, attention_mask=mask, token_type_ids=seg).logits`` in eval mode.
+
+    ``state`` uses HF key names (``bert.embeddings.word_embeddings.weight`` ...); ids/mask/seg ``[N,L]`` int64."""
+    x = bert_hidden_states(state, ids, mask, seg, num_heads, eps)[-1]
+    pooled = torch.tanh(F.linear(x[:, 0], state["bert.pooler.dense.weight"], state["bert.pooler.dense.bias"]))
+    return F.linear(pooled, state["classifier.weight"], state["classifier.bias"])
+
+
+# --------------------------------------------------------------------------------------------------
+# CEDR-KNRM   (reranker/CEDRKNRM.py:85-171)   -- SURVEY.md §8(f) rank 2
+# --------------------------------------------------------------------------------------------------
+def cedr_masked_simmat(emb, bert_mask, bert_seg, maxqlen_plus1: int):
+    """``masked_simmats`` + ``_cos_simmat`` (CEDRKNRM.py:85-108) on ``emb [N, L-1, H]`` ([CLS] already removed)."""
+    query_mask = bert_mask * (bert_seg == 0).to(emb.dtype)
+    padded_query = (query_mask.unsqueeze(2) * emb)[:, :maxqlen_plus1]
+    query_mask = query_mask[:, :maxqlen_plus1]
+    doc_mask = bert_mask * (bert_seg == 1).to(emb.dtype)
+    padded_doc = doc_mask.unsqueeze(2) * emb
+    a_den = padded_query.norm(p=2, dim=2)[:, :, None] + 1e-9
+    b_den = padded_doc.norm(p=2, dim=2)[:, None, :] + 1e-9
+    sim = padded_query.bmm(padded_doc.permute(0, 2, 1)) / (a_den * b_den)
+    sim = sim * query_mask[:, :, None] * doc_mask[:, None, :]
+    return sim, doc_mask, query_mask
+
+
+def cedr_knrm_features(hidden, bert_mask, bert_seg, batch_size, num_passages, maxqlen_plus1, mus, sigmas) -> torch.Tensor:
+    """``CEDRKNRM_Class.knrm`` (CEDRKNRM.py:110-136) for one layer's hidden states ``[B*P, L, H]`` -> ``[B, K]``."""
+    fm = bert_mask[:, 1:].to(hidden.dtype)
+    sim, doc_mask, query_mask = cedr_masked_simmat(hidden[:, 1:], fm, bert_seg[:, 1:], maxqlen_plus1)
+    Lm1 = sim.shape[2]
+    sim = sim.view(batch_size, num_passages, maxqlen_plus1, Lm1)
+    doc_mask = doc_mask.view(batch_size, num_passages, 1, Lm1)
+    doc_simmat = torch.cat([sim[:, p] for p in range(num_passages)], dim=2)
+    dmask = torch.cat([doc_mask[:, p] for p in range(num_passages)], dim=2)
+    qmask = query_mask.view(batch_size, num_passages, -1, 1)[:, 0]
+    kern = torch.stack([torch.exp(-0.5 * (doc_simmat - m) * (doc_simmat - m) / s / s) for m, s in zip(mus, sigmas)], dim=1)
+    kern = kern * dmask.view(batch_size, 1, 1, -1) * qmask.view(batch_size, 1, -1, 1)
+    feats = kern.sum(dim=3)
+    feats = torch.log(torch.clamp(feats, min=1e-10)) * 0.01
+    return feats.sum(dim=2)
+
+
+def cedrknrm_forward(state: dict, bert_input, bert_mask, bert_seg, num_heads: int, maxqlen: int, simmat_layers, cls="avg",
+                     combine_hidden=1024, eps: float = 1e-12) -> torch.Tensor:
+    """``CEDRKNRM_Class.forward`` (CEDRKNRM.py:138-171) -> ``[B,1]``; inputs ``[B,P,L]`` int64; ``state`` = the module's state_dict
+    (encoder under ``bert.``, ``kernels.kernels.{i}.mu|sigma``, ``combine.{0,1}``)."""
+    B, P, L = bert_input.shape
+    flat = lambda t: t.reshape(B * P, L)
+    ids, mask, seg = flat(bert_input), flat(bert_mask), flat(bert_seg)
+    hidden = bert_hidden_states(state, ids, mask, seg, num_heads, eps)
+    kp = knrm_params_from_state(state)
+    feats = []
+    if cls:
+        c = hidden[-1][:, 0, :].view(B, P, -1)
+        feats.append(c.max(dim=1)[0] if cls == "max" else c.mean(dim=1))
+    if -1 not in simmat_layers:
+        feats += [cedr_knrm_features(hidden[l], mask, seg, B, P, maxqlen + 1, kp["mus"], kp["sigmas"]) for l in simmat_layers]
+    x = torch.cat(feats, dim=1)
+    x = F.linear(x, state["combine.0.weight"], state["combine.0.bias"])
+    if combine_hidden:
+        x = F.linear(x, state["combine.1.weight"], state["combine.1.bias"])
+    return x
 
 
 def bert_maxp_aggregate(passage_scores, doc_mask, doc_seg, aggregation="max") -> torch.Tensor:

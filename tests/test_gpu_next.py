@@ -135,3 +135,61 @@ def test_convknrm_projection_follows_weight_updates():
         assert not torch.equal(s0, s1)
         model.convs[1][0].weight.mul_(-1.0)
         assert torch.equal(rr.test(b), s0)
+
+
+# ---- CEDR-KNRM -------------------------------------------------------------------------------------
+class BertExtractor:
+    def __init__(self, P, L, maxqlen):
+        self.embeddings = None
+        self.config = {"numpassages": P, "maxseqlen": L, "maxqlen": maxqlen}
+
+
+def _build_cedr(name, variant):
+    import json
+
+    from capreolus_b200 import reranker as R
+
+    g = load_golden(f"cedrknrm_{name}")
+    cfg = json.loads(str(g["config_json"]))
+    vcfg = json.loads(str(g[f"{variant}/config_json"]))
+    N, P, L, maxqlen = (int(x) for x in g["shape"])
+    keep = ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size", "vocab_size", "max_position_embeddings",
+            "type_vocab_size", "initializer_range", "layer_norm_eps", "hidden_act")
+    torch.manual_seed(int(g["weight_seed"]))
+    rr = R.CEDRKNRM(dict(pretrained={k: cfg[k] for k in keep if k in cfg}, **vcfg), provide={"extractor": BertExtractor(P, L, maxqlen)})
+    model = rr.build_model()
+    tot = sum(float(v.double().abs().sum()) for v in model.bert.state_dict().values() if v.dtype.is_floating_point)
+    np.testing.assert_allclose(tot, g["weight_checksum"][0], rtol=1e-9)  # same random-init encoder as the golden's
+    missing, unexpected = model.load_state_dict(golden_state(g, variant), strict=False)
+    assert not unexpected and all(k.startswith("bert.") or k in ("one", "zero") for k in missing), (missing, unexpected)
+    model.to(DEV).eval()
+    batch = {k: torch.from_numpy(g[k].astype(np.int64)).to(DEV) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+    return g, rr, model, batch
+
+
+@pytest.mark.parametrize("name,variants", [("tiny", ["default", "nocls", "clsonly"]), ("mid", ["default", "nocls"]), ("base", ["default", "nocls"])])
+def test_cedrknrm_scores_match_reference(name, variants):
+    for variant in variants:
+        g, rr, model, b = _build_cedr(name, variant)
+        scores = rr.test(b).cpu().numpy()
+        assert scores.shape == g[f"{variant}/scores"].shape
+        assert rel_err(scores, g[f"{variant}/scores"], floor=1e-2) < TOL, variant
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid", "base"])
+def test_cedrknrm_features_match_reference(name):
+    g, rr, model, b = _build_cedr(name, "default")
+    feats = model.features(b["pos_bert_input"], b["pos_mask"], b["pos_seg"]).cpu().numpy()
+    assert feats.shape == g["feats"].shape
+    # absolute: cls features are LayerNorm outputs (|x| ~ 1), knrm features are 0.01 * log sums (|x| ~ 1)
+    np.testing.assert_allclose(feats, g["feats"], atol=2e-3)
+
+
+def test_cedrknrm_doc_chunking_is_invisible():
+    g, rr, model, b = _build_cedr("tiny", "default")
+    whole = rr.test(b)
+    model.max_seqs_per_call, model._engine = 3, None  # one document (3 passages) per encoder call
+    assert torch.equal(rr.test(b), whole)
+    model.train()
+    with pytest.raises(NotImplementedError):
+        rr.test(b)

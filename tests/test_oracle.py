@@ -198,3 +198,38 @@ def test_convknrm_scores(shape, variant):
         kp = restated.knrm_params_from_state(st)
         feats = restated.convknrm_features(st, table, tb["posdoc"], tb["query"], 3, True, kp["mus"], kp["sigmas"]).numpy()
         np.testing.assert_allclose(feats, g["feats"], rtol=1e-4, atol=1e-3)
+
+
+# ---- CEDR-KNRM ---------------------------------------------------------------------------------
+def _cedr_state(g, variant):
+    """The reference module's state_dict: combine / kernels from the golden, the encoder re-derived from its seed."""
+    import json
+
+    import transformers
+
+    cfg = json.loads(str(g["config_json"]))
+    keep = ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size", "vocab_size", "max_position_embeddings",
+            "type_vocab_size", "initializer_range", "layer_norm_eps", "hidden_act")
+    torch.manual_seed(int(g["weight_seed"]))
+    bert = transformers.BertModel(transformers.BertConfig(**{k: cfg[k] for k in keep if k in cfg})).eval()
+    tot = sum(float(v.double().abs().sum()) for v in bert.state_dict().values() if v.dtype.is_floating_point)
+    np.testing.assert_allclose(tot, g["weight_checksum"][0], rtol=1e-9)
+    state = {f"bert.{k}": v for k, v in bert.state_dict().items()}
+    state.update(golden_state(g, variant))
+    return state, cfg
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid", "base"])
+def test_cedrknrm_scores(name):
+    import json
+
+    g = load_golden(f"cedrknrm_{name}")
+    N, P, L, maxqlen = (int(x) for x in g["shape"])
+    tb = {k: torch.from_numpy(g[k].astype(np.int64)) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+    for variant in [k.split("/")[0] for k in g if k.endswith("/scores")]:
+        state, cfg = _cedr_state(g, variant)
+        vcfg = json.loads(str(g[f"{variant}/config_json"]))
+        with torch.no_grad():
+            got = restated.cedrknrm_forward(state, tb["pos_bert_input"], tb["pos_mask"], tb["pos_seg"], cfg["num_attention_heads"], maxqlen,
+                                            vcfg["simmat_layers"], vcfg["cls"], vcfg["combine_hidden"]).view(-1).numpy()
+        assert rel_err(got, g[f"{variant}/scores"], floor=1e-2) < 1e-4, variant
