@@ -33,13 +33,14 @@ Q, D, V, E = synthetic.MAXQLEN, synthetic.MAXDOCLEN, synthetic.VOCAB, synthetic.
 # ids (32+512)*8 B + gathered rows 544*300*4 B + one fp32 score
 ALGO_BYTES_PER_PAIR = (Q + D) * 8 + (Q + D) * E * 4 + 4
 BERT_L = 512
+ENCODERS = ("bert", "cedrknrm")  # models whose hot path is the BERT encoder (tensor-pipe roofline)
 # per layer 2*12*768^2*512 (Linear layers) + 2*2*512^2*768 (attention) = 8.05 GFLOP; x12 layers = 96.6 GFLOP
 BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
-MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM"}
-DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000}
-DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500}
+MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM"}
+DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512}
+DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500, "cedrknrm": 128}
 TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)",
-              "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
+              "cedrknrm": "gemm_kernel<3> (+ attention_tc2_kernel, cedr_pool_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
 
 
@@ -99,7 +100,9 @@ def build_reranker(model_key):
     from capreolus_b200 import reranker as R
 
     torch.manual_seed(0)
-    if model_key == "bert":
+    if model_key == "cedrknrm":
+        rr = R.CEDRKNRM(dict(pretrained={}, simmat_layers="0..12,1", cls="avg"), provide={"extractor": Extractor(numpassages=1, maxseqlen=BERT_L, maxqlen=Q)})
+    elif model_key == "bert":
         rr = R.PTBERTMaxP(dict(pretrained={}, aggregation="max", hidden_dropout_prob=0.1), provide={"extractor": Extractor(numpassages=1, maxseqlen=BERT_L)})
     else:
         rr = getattr(R, MODELS[model_key])({}, provide={"extractor": Extractor(synthetic.embedding_table(V, E, seed=0), maxqlen=Q, maxdoclen=D)})
@@ -107,7 +110,7 @@ def build_reranker(model_key):
 
 
 def host_batch(model_key, n, seed):
-    if model_key == "bert":
+    if model_key in ENCODERS:
         b = synthetic.bert_batch(n, seqlen=BERT_L, qlen=Q, seed=seed, numpassages=1, ragged=False)
     else:
         b = synthetic.throughput_batch(n, Q, D, V, seed=seed)
@@ -124,6 +127,15 @@ def cpu_reference_step(model_key, state):
     from oracle import restated
 
     torch.set_num_threads(os.cpu_count() or 1)
+    if model_key == "cedrknrm":
+        b = host_batch("cedrknrm", 4, seed=3)
+
+        def step():
+            with torch.no_grad():
+                restated.cedrknrm_forward(state, b["pos_bert_input"], b["pos_mask"], b["pos_seg"], 12, Q, list(range(13)), "avg", 1024)
+            return 4
+
+        return step, "oracle/restated.cedrknrm_forward (reference op sequence: BERT-base hidden states, 13 masked cosine matrices, kernel pooling), B=4, L=512"
     if model_key == "bert":
         import transformers
 
@@ -175,7 +187,7 @@ def run_reference(args):
     rr, model = build_reranker(args.model) if args.model != "bert" else (None, None)
     state = {k: v.detach().clone() for k, v in model.state_dict().items()} if model is not None else None
     step, what = cpu_reference_step(args.model, state)
-    per_step_calls = 8 if args.model != "bert" else 2  # 512 pairs (KNRM family) / 16 sequences (BERT) per step
+    per_step_calls = 8 if args.model not in ENCODERS else (2 if args.model == "bert" else 4)  # 512 pairs (KNRM family) / 16 sequences (encoders) per step
     for _ in range(args.warmup):
         step()
     t0, pairs = time.perf_counter(), 0
@@ -283,7 +295,7 @@ def main():
         assert torch.equal(out.to(dev), mine), "pipelined predict != direct test"
         # ---- end to end from a packed, device-resident id store: only (query, doc) indices cross PCIe ----
         packed_ms = None
-        if args.model != "bert":
+        if args.model not in ENCODERS:
             from capreolus_b200.predict import PackedIdStore, PairAssembler, RunPredictor
 
             t = pinned.tensors
@@ -315,15 +327,15 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        if args.model == "bert":
+        if args.model in ENCODERS:
             achieved = BERT_FLOPS_PER_PAIR * n / (kernel_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
-                    "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)", "kernel": TOP_KERNEL["bert"],
+                    "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)", "kernel": TOP_KERNEL[args.model],
                     "algorithmic_flops_per_pair": BERT_FLOPS_PER_PAIR, "issued_tensor_flops_per_pair": 3 * BERT_FLOPS_PER_PAIR,
                     "note": "achieved counts ALGORITHMIC flops over the whole forward; the bf16x3 parity mode issues 3 tensor-core products per "
                             "algorithmic flop (Linear layers and attention)", "forward_ms": kernel_ms, "pairs_per_forward": n}
-            launches = args.steps * (2 + 12 * 7) * ((n + 127) // 128)
-            workload = (f"monoBERT (BERT-base, random init) forward, {n} synthetic pairs per GPU per step, L={BERT_L} (|q|={Q}, doc truncated to "
+            launches = args.steps * ((2 + 12 * 7) * ((n + 127) // 128) if args.model == "bert" else (1 + 12 * 7 + 3) * ((n + 63) // 64))
+            workload = (f"{'monoBERT' if args.model == 'bert' else 'CEDR-KNRM (13 similarity layers, cls=avg) on'} (BERT-base, random init) forward, {n} synthetic pairs per GPU per step, L={BERT_L} (|q|={Q}, doc truncated to "
                         f"{BERT_L - Q - 3}), bf16x3 parity mode; bounded sample of BASELINE.json configs[3] (1000 q x 1000 docs)")
             l2 = "activations of one 128-sequence chunk (~2 GB) exceed L2; weights (0.35 GB as bf16 hi/lo planes) stream from HBM/L2"
         else:
@@ -343,7 +355,7 @@ def main():
             "metric": f"query-doc pairs scored/sec (|q|={Q},|d|={D})",
             "value": n_total * args.steps / (elapsed_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.model != "bert" else "bf16x3 (fp32 accumulate)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if args.model not in ENCODERS else "bf16x3 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": workload, "pairs_per_gpu": n, "l2_policy": l2,
                        "parallelism": f"pairs sharded over {world} GPU(s), one all-gather of scores per step" if world > 1 else "single GPU"},
             "roofline": roof,

@@ -15,15 +15,15 @@
 //   cedr_finish_kernel  per (doc, layer): sum the partial soft-TFs over the doc's passages, log(clamp(., 1e-10)) * 0.01,
 //                       sum over ALL maxqlen+1 query rows (masked rows contribute log(1e-10) * 0.01 like the reference);
 //                       also the [CLS] feature (mean / max over passages of the last hidden state).
-//   linear2_kernel      `combine`: Linear(F, hidden) -> Linear(hidden, 1) (no activation in between), or Linear(F, 1).
+//   linear_rows / linear_out   `combine`: Linear(F, hidden) -> Linear(hidden, 1) (no activation in between), or Linear(F, 1).
 #include "common.cuh"
 
 namespace capr {
 
 constexpr int CEDR_MAXQ = 64;    // maxqlen + 1 query rows
-constexpr int CEDR_MAXK = 32;    // kernels
+constexpr int CEDR_MAXK = 16;    // kernels (lane k and lane 16+k evaluate kernel k for the two doc tokens in flight)
 constexpr int CEDR_MAXH = 1024;  // hidden size (lane owns 4 floats per 128-float slab: <= 8 slabs)
-constexpr int CEDR_WARPS = 8;
+constexpr int CEDR_WARPS = 16;  // one CTA per SM (the query block is ~100 KB): 16 warps hide the global-load / shuffle latencies
 
 struct CedrPoolArgs {
   const float* hidden;   // [n_layers][T][H]
@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(CEDR_WARPS * 32) cedr_pool_kernel(const CedrPo
   }
   __syncthreads();
   float mu = 0.f, cc = 0.f;
-  if (lane < a.K) {
-    const float sg = a.sigma[lane];
-    mu = a.mu[lane];
+  if ((lane & 15) < a.K) {  // lanes k and 16+k both hold kernel k (K <= 16 on this path, checked on the host)
+    const float sg = a.sigma[lane & 15];
+    mu = a.mu[lane & 15];
     cc = -0.5f * 1.4426950408889634f / (sg * sg);
   }
   float* my_acc = acc + (size_t)warp * a.Qm * CEDR_MAXK;
@@ -115,14 +115,18 @@ __global__ void __launch_bounds__(CEDR_WARPS * 32) cedr_pool_kernel(const CedrPo
         p0 = fmaf(qq.x, d0[c].x, p0), p0 = fmaf(qq.y, d0[c].y, p0), p0 = fmaf(qq.z, d0[c].z, p0), p0 = fmaf(qq.w, d0[c].w, p0);
         p1 = fmaf(qq.x, d1[c].x, p1), p1 = fmaf(qq.y, d1[c].y, p1), p1 = fmaf(qq.z, d1[c].z, p1), p1 = fmaf(qq.w, d1[c].w, p1);
       }
-      p0 = warp_sum(p0) * inv0;  // cosine (0 when this passage's own query mask zeroed the row)
-      p1 = warp_sum(p1) * inv1;
-      if (lane < a.K) {
-        float e = 0.f;
-        if (live0) e += ex2_approx(cc * (p0 - mu) * (p0 - mu));
-        if (live1) e += ex2_approx(cc * (p1 - mu) * (p1 - mu));
-        my_acc[i * CEDR_MAXK + lane] += e;
-      }
+      // two reductions for the price of one: after the first exchange lanes 0-15 carry p0, lanes 16-31 carry p1
+      const bool upper = (lane & 16) != 0;
+      float v = upper ? p1 : p0;
+      v += __shfl_xor_sync(0xffffffffu, upper ? p0 : p1, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float cosv = v * (upper ? inv1 : inv0);  // cosine (0 when this passage's own query mask zeroed the row)
+      // lane k (p0) and lane 16+k (p1) evaluate kernel k
+      const float adj = cosv - mu;
+      float e = ((upper ? live1 : live0) && (lane & 15) < a.K) ? ex2_approx(cc * adj * adj) : 0.f;
+      e += __shfl_down_sync(0xffffffffu, e, 16);
+      if (lane < a.K) my_acc[i * CEDR_MAXK + lane] += e;
     }
   }
   __syncthreads();
@@ -171,28 +175,32 @@ __global__ void __launch_bounds__(256) cedr_finish_kernel(const CedrFinishArgs a
   }
 }
 
-// out[b] = w2 . (W1 x_b + b1) + b2   (hidden > 0)    or    W1 x_b + b1   (hidden == 0, W1 [1,F])
-__global__ void __launch_bounds__(256) linear2_kernel(const float* __restrict__ x, int F, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                      int hidden, const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out) {
-  __shared__ float part[8];
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// `combine`: hvals[b][h] = W1[h] . x_b + b1[h] (one warp per (b, h); W1 rows are shared by all b through L2), then
+// out[b] = w2 . hvals[b] + b2 (hidden > 0) or hvals[b][0] (hidden == 0, W1 [1,F]).  Fixed summation order.
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ x, int F, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          int rows, float* __restrict__ hvals) {
+  const int h = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
+  if (h >= rows) return;
+  const float* w = w1 + (size_t)h * F;
   const float* xb = x + (size_t)b * F;
-  float acc = 0.f;
-  const int rows = hidden > 0 ? hidden : 1;
-  for (int h = warp; h < rows; h += 8) {
-    const float* w = w1 + (size_t)h * F;
-    float p = 0.f;
-    for (int i = lane; i < F; i += 32) p = fmaf(w[i], xb[i], p);
-    p = warp_sum(p) + b1[h];
-    acc += hidden > 0 ? w2[h] * p : p;
+  float p = 0.f;
+  for (int i = lane; i < F; i += 32) p = fmaf(w[i], xb[i], p);
+  p = warp_sum(p);
+  if (lane == 0) hvals[(size_t)b * rows + h] = p + b1[h];
+}
+
+__global__ void __launch_bounds__(128) linear_out_kernel(const float* __restrict__ hvals, int rows, int hidden, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, int B, float* __restrict__ out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  if (hidden == 0) {
+    if (lane == 0) out[b] = hvals[b];
+    return;
   }
-  if (lane == 0) part[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += part[w];
-    out[b] = t + (hidden > 0 ? b2[0] : 0.f);
-  }
+  float p = 0.f;
+  for (int h = lane; h < rows; h += 32) p = fmaf(w2[h], hvals[(size_t)b * rows + h], p);
+  p = warp_sum(p);
+  if (lane == 0) out[b] = p + b2[0];
 }
 
 }  // namespace capr
@@ -203,9 +211,13 @@ extern "C" {
 
 int capr_cedrknrm_feature_dim(int H, int n_layers, int K, int cls_mode) { return (cls_mode ? H : 0) + n_layers * K; }
 
-size_t capr_cedrknrm_workspace_bytes(int n_seq, int maxqlen, int n_layers, int K) {
-  if (n_seq <= 0 || maxqlen <= 0 || n_layers < 0 || K <= 0) return 0;
-  return (size_t)n_layers * n_seq * (maxqlen + 1) * K * sizeof(float);
+static size_t cedr_partial_bytes(int n_seq, int maxqlen, int n_layers, int K) {
+  return (((size_t)n_layers * n_seq * (maxqlen + 1) * K * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+size_t capr_cedrknrm_workspace_bytes(int n_seq, int maxqlen, int n_layers, int K, int combine_hidden) {
+  if (n_seq <= 0 || maxqlen <= 0 || n_layers < 0 || K <= 0 || combine_hidden < 0) return 0;
+  return cedr_partial_bytes(n_seq, maxqlen, n_layers, K) + (size_t)n_seq * (combine_hidden > 0 ? combine_hidden : 1) * sizeof(float);
 }
 
 int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidden, const int64_t* mask, const int64_t* seg, int B, int P, int L,
@@ -225,7 +237,7 @@ int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidd
                "%s: null pointer", fn);
   CAPR_REQUIRE(!scores || (w1 && b1 && (combine_hidden == 0 || (w2 && b2))), CAPR_ERR_BAD_POINTER, "%s: scores requested without combine weights", fn);
   const int n_seq = B * P;
-  CAPR_REQUIRE(n_layers == 0 || workspace_bytes >= capr_cedrknrm_workspace_bytes(n_seq, maxqlen, n_layers, K), CAPR_ERR_BAD_SHAPE,
+  CAPR_REQUIRE(workspace && workspace_bytes >= capr_cedrknrm_workspace_bytes(n_seq, maxqlen, n_layers, K, combine_hidden), CAPR_ERR_BAD_SHAPE,
                "%s: workspace too small (capr_cedrknrm_workspace_bytes)", fn);
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
@@ -253,7 +265,11 @@ int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidd
   CAPR_CHECK_CUDA(cudaGetLastError());
   if (scores) {
     const int F = capr_cedrknrm_feature_dim(H, n_layers, K, cls_mode);
-    linear2_kernel<<<B, 256, 0, st>>>(feats, F, w1, b1, combine_hidden, w2, b2, scores);
+    const int rows = combine_hidden > 0 ? combine_hidden : 1;
+    float* hvals = (float*)((unsigned char*)workspace + cedr_partial_bytes(n_seq, maxqlen, n_layers, K));
+    linear_rows_kernel<<<dim3((rows + 7) / 8, B), 256, 0, st>>>(feats, F, w1, b1, rows, hvals);
+    CAPR_CHECK_CUDA(cudaGetLastError());
+    linear_out_kernel<<<(B + 3) / 4, 128, 0, st>>>(hvals, rows, combine_hidden, w2, b2, B, scores);
     CAPR_CHECK_CUDA(cudaGetLastError());
   }
   return CAPR_OK;

@@ -93,7 +93,7 @@ class CEDRKNRM_Class(nn.Module):
         self.one = nn.Parameter(torch.ones(1), requires_grad=False)
         self.zero = nn.Parameter(torch.zeros(1), requires_grad=False)
         self.precision = config.get("precision", "bf16x3") if hasattr(config, "get") else "bf16x3"
-        self.max_seqs_per_call = 64
+        self.max_seqs_per_call = 128
         self._engine, self._engine_key, self._head_ws = None, None, None
 
     def engine(self) -> BertEngine:
@@ -132,7 +132,7 @@ class CEDRKNRM_Class(nn.Module):
             nb = min(docs_per_call, B - lo)
             sl = slice(lo * P, (lo + nb) * P)
             hs = eng.hidden_states(ids[sl], mask[sl], seg[sl], want)  # [len(want), nb*P*L, H]
-            need = lib.capr_cedrknrm_workspace_bytes(nb * P, self.maxqlen - 1, len(layers), K)
+            need = lib.capr_cedrknrm_workspace_bytes(nb * P, self.maxqlen - 1, len(layers), K, hidden)
             if self._head_ws is None or self._head_ws.numel() < need or self._head_ws.device != ids.device:
                 self._head_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=ids.device)
             _lib.check(lib.capr_cedrknrm_head(

@@ -245,10 +245,10 @@ int capr_bert_forward_hidden(capr_bert_t handle, const int64_t* ids, const int64
  *   log(clamp(., 1e-10)) * 0.01, summed over the maxqlen+1 query rows -> K features per layer.
  *   cls_mode: 0 none, 1 avg, 2 max over the passages.   feats [B, F], F = capr_cedrknrm_feature_dim (cls first).
  *   combine: w1 [combine_hidden or 1, F], b1; w2 [1, combine_hidden], b2 (combine_hidden == 0: single Linear(F,1)).
- *   scores [B] (nullable).  workspace: capr_cedrknrm_workspace_bytes(B*P, maxqlen, n_layers, K).
- * Limits: maxqlen < 64, K <= 32, H <= 1024 and a multiple of 4. */
+ *   scores [B] (nullable).  workspace: capr_cedrknrm_workspace_bytes(B*P, maxqlen, n_layers, K, combine_hidden).
+ * Limits: maxqlen < 64, K <= 16, H <= 1024 and a multiple of 4. */
 int capr_cedrknrm_feature_dim(int H, int n_layers, int K, int cls_mode);
-size_t capr_cedrknrm_workspace_bytes(int n_seq, int maxqlen, int n_layers, int K);
+size_t capr_cedrknrm_workspace_bytes(int n_seq, int maxqlen, int n_layers, int K, int combine_hidden);
 int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidden, const int64_t* mask, const int64_t* seg, int B,
                        int P, int L, int H, int maxqlen, const float* mu, const float* sigma, int K, int cls_mode, const float* w1,
                        const float* b1, int combine_hidden, const float* w2, const float* b2, float* feats, float* scores,
