@@ -76,6 +76,8 @@ SIGNATURES = {
     "capr_cedrknrm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "capr_cedrknrm_head": (c_int, [_f32p, c_int, _f32p, _i64p, _i64p, c_int, c_int, c_int, c_int, c_int, _f32p, _f32p, c_int, c_int, _f32p, _f32p,
                                    c_int, _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
+    "capr_parade_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "capr_parade_head": (c_int, [c_void_p, _f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
 }

@@ -519,14 +519,17 @@ size_t capr_bert_workspace_bytes(capr_bert_t h, int n_seq, int L) {
 
 // Shared body of capr_bert_forward / capr_bert_forward_hidden.  hidden_layers[i] in [0, layers]: 0 = embedding output,
 // l = output of encoder layer l (HF `hidden_states[l]`); the fp32 activations are copied to hidden_out[i] ([T,H] each).
+// x_in (nullable): fp32 [T,H] input of the first encoder layer; replaces the embedding stage (ids / seg are then unused) --
+// the PARADE aggregator feeds passage [CLS] vectors to two stand-alone BertLayers (ptparade.py:55-68).
 static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, float* logits,
-                    const int* hidden_layers, int n_hidden, float* hidden_out, void* workspace, size_t workspace_bytes, capr_stream_t stream) {
+                    const int* hidden_layers, int n_hidden, float* hidden_out, void* workspace, size_t workspace_bytes, capr_stream_t stream,
+                    const float* x_in = nullptr) {
   Model* m = (Model*)h;
   CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
   CAPR_REQUIRE(n_seq >= 0 && L > 0 && n_hidden >= 0, CAPR_ERR_BAD_SHAPE, "%s: n_seq=%d L=%d", fn, n_seq, L);
   if (n_seq == 0) return CAPR_OK;
-  CAPR_REQUIRE(L <= m->cfg.max_pos, CAPR_ERR_BAD_SHAPE, "%s: sequence length %d exceeds max_position_embeddings %d", fn, L, m->cfg.max_pos);
-  CAPR_REQUIRE(ids && mask && seg && (logits || n_hidden > 0) && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(x_in || L <= m->cfg.max_pos, CAPR_ERR_BAD_SHAPE, "%s: sequence length %d exceeds max_position_embeddings %d", fn, L, m->cfg.max_pos);
+  CAPR_REQUIRE((x_in || (ids && seg)) && mask && (logits || n_hidden > 0) && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(n_hidden == 0 || (hidden_layers && hidden_out), CAPR_ERR_BAD_POINTER, "%s: hidden states requested without buffers", fn);
   for (int i = 0; i < n_hidden; ++i)
     CAPR_REQUIRE(hidden_layers[i] >= 0 && hidden_layers[i] <= m->cfg.layers, CAPR_ERR_BAD_SHAPE, "%s: hidden layer %d not in [0, %d]", fn, hidden_layers[i], m->cfg.layers);
@@ -557,9 +560,15 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     CAPR_CHECK_CUDA(cudaMemsetAsync(ws.ffn_lo + T * I, 0, (Tp - T) * I * 2, st));
   }
   const int row_blocks = (Ti + 7) / 8;  // 8 warps (rows) per 256-thread CTA
-  embed_ln_kernel<<<row_blocks, 256, 0, st>>>((const long long*)ids, (const long long*)seg, Ti, L, H, m->cfg.vocab, m->cfg.max_pos,
-                                              m->cfg.type_vocab, m->word, m->pos, m->type, m->emb_g, m->emb_b, m->cfg.ln_eps, ws.x, ws.x_hi,
-                                              ws.x_lo);
+  if (x_in) {
+    CAPR_CHECK_CUDA(cudaMemcpyAsync(ws.x, x_in, T * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const size_t n = T * H;
+    split_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(x_in, n, ws.x_hi, ws.x_lo);
+  } else {
+    embed_ln_kernel<<<row_blocks, 256, 0, st>>>((const long long*)ids, (const long long*)seg, Ti, L, H, m->cfg.vocab, m->cfg.max_pos,
+                                                m->cfg.type_vocab, m->word, m->pos, m->type, m->emb_g, m->emb_b, m->cfg.ln_eps, ws.x, ws.x_hi,
+                                                ws.x_lo);
+  }
   CAPR_CHECK_CUDA(cudaGetLastError());
   auto emit_hidden = [&](int layer_index) -> int {
     for (int i = 0; i < n_hidden; ++i)
@@ -630,6 +639,83 @@ int capr_bert_forward(capr_bert_t h, const int64_t* ids, const int64_t* mask, co
 int capr_bert_forward_hidden(capr_bert_t h, const int64_t* ids, const int64_t* mask, const int64_t* seg, int n_seq, int L, const int* hidden_layers,
                              int n_hidden, float* hidden_out, float* logits, void* workspace, size_t workspace_bytes, capr_stream_t stream) {
   return bert_run("capr_bert_forward_hidden", h, ids, mask, seg, n_seq, L, logits, hidden_layers, n_hidden, hidden_out, workspace, workspace_bytes, stream);
+}
+
+// ---- PARADE aggregation head: ptparade.py:55-78 ---------------------------------------------------
+}  // extern "C"
+
+namespace capr {
+namespace bert {
+
+// merged[b][0] = initial_cls + pos[0];  merged[b][1+p] = last_hidden[(b*P+p)*L + 0] + pos[1+p]      (ptparade.py:57-62)
+__global__ void __launch_bounds__(256) parade_merge_kernel(const float* __restrict__ last_hidden, int B, int P, int L, int H,
+                                                           const float* __restrict__ initial_cls, const float* __restrict__ pos,
+                                                           float* __restrict__ merged, long long* __restrict__ ones) {
+  const int row = blockIdx.x;  // b*(P+1) + j
+  const int b = row / (P + 1), j = row - b * (P + 1);
+  const float* src = j == 0 ? initial_cls : last_hidden + ((size_t)b * P + (j - 1)) * L * H;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) merged[(size_t)row * H + h] = src[h] + pos[(size_t)j * H + h];
+  if (threadIdx.x == 0) ones[row] = 1;
+}
+
+// score[b] = w . x[b*(P+1) + 0] + bias      (ptparade.py:66-67,78)
+__global__ void __launch_bounds__(128) parade_score_kernel(const float* __restrict__ x, int B, int rows_per_doc, int H, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ scores) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = x + (size_t)b * rows_per_doc * H;
+  float p = 0.f;
+  for (int h = lane; h < H; h += 32) p = fmaf(w[h], row[h], p);
+  p = warp_sum(p);
+  if (lane == 0) scores[b] = p + bias[0];
+}
+
+static size_t parade_extra_bytes(const capr_bert_config& c, size_t rows) {
+  return align256(rows * c.hidden * 4) * 2 + align256(rows * 8);  // merged input, aggregator output, all-ones mask
+}
+
+}  // namespace bert
+}  // namespace capr
+
+extern "C" {
+
+size_t capr_parade_workspace_bytes(capr_bert_t agg, int B, int P) {
+  Model* m = (Model*)agg;
+  if (!m || B <= 0 || P <= 0) return 0;
+  const size_t rows = (size_t)B * (P + 1);
+  return carve(m->cfg, rows, nullptr, nullptr) + parade_extra_bytes(m->cfg, rows);
+}
+
+int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, int L, const float* initial_cls, const float* pos_emb,
+                     const float* lin_w, const float* lin_b, float* scores, float* aggregated, void* workspace, size_t workspace_bytes,
+                     capr_stream_t stream) {
+  const char* fn = "capr_parade_head";
+  Model* m = (Model*)agg;
+  CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
+  CAPR_REQUIRE(B >= 0 && P > 0 && L > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d P=%d L=%d", fn, B, P, L);
+  if (B == 0) return CAPR_OK;
+  CAPR_REQUIRE(last_hidden && initial_cls && pos_emb && lin_w && lin_b && scores && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(((uintptr_t)workspace & 255) == 0, CAPR_ERR_BAD_POINTER, "%s: workspace must be 256-byte aligned", fn);
+  const int H = m->cfg.hidden;
+  const size_t rows = (size_t)B * (P + 1);
+  const size_t enc = carve(m->cfg, rows, nullptr, nullptr);
+  CAPR_REQUIRE(workspace_bytes >= enc + parade_extra_bytes(m->cfg, rows), CAPR_ERR_BAD_SHAPE, "%s: workspace too small (capr_parade_workspace_bytes)", fn);
+  unsigned char* p = (unsigned char*)workspace + enc;
+  float* merged = (float*)p;
+  float* out = (float*)(p + align256(rows * H * 4));
+  long long* ones = (long long*)(p + 2 * align256(rows * H * 4));
+  cudaStream_t st = (cudaStream_t)stream;
+  parade_merge_kernel<<<(unsigned)rows, 256, 0, st>>>(last_hidden, B, P, L, H, initial_cls, pos_emb, merged, ones);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  const int last_layer[1] = {m->cfg.layers};
+  // the two BertLayers see no attention mask (ptparade.py:64-65): all-ones mask, sequences of P+1 vectors
+  const int rc = bert_run(fn, agg, nullptr, (const int64_t*)ones, nullptr, B, P + 1, nullptr, last_layer, 1, out, workspace, enc, stream, merged);
+  if (rc) return rc;
+  parade_score_kernel<<<(B + 3) / 4, 128, 0, st>>>(out, B, P + 1, H, lin_w, lin_b, scores);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  if (aggregated)  // transformer_out_2[:, 0, :] (tests)
+    CAPR_CHECK_CUDA(cudaMemcpy2DAsync(aggregated, (size_t)H * 4, out, (size_t)(P + 1) * H * 4, (size_t)H * 4, B, cudaMemcpyDeviceToDevice, st));
+  return CAPR_OK;
 }
 
 // Debug / test entry: C = A . W^T + bias through the same tcgen05 kernel (A [M,K], W [N,K], fp32 device buffers).

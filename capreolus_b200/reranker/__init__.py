@@ -58,5 +58,6 @@ from capreolus_b200.reranker.ptBERTMaxP import PTBERTMaxP, PTBERTMaxP_Class  # n
 from capreolus_b200.reranker.DRMMTKS import DRMMTKS, DRMMTKS_class  # noqa: E402,F401
 from capreolus_b200.reranker.ConvKNRM import ConvKNRM, ConvKNRM_class  # noqa: E402,F401
 from capreolus_b200.reranker.CEDRKNRM import CEDRKNRM, CEDRKNRM_Class  # noqa: E402,F401
+from capreolus_b200.reranker.ptparade import PTParade, PTParade_Class  # noqa: E402,F401
 
-__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class", "DRMMTKS", "DRMMTKS_class", "ConvKNRM", "ConvKNRM_class", "CEDRKNRM", "CEDRKNRM_Class"]
+__all__ = ["Reranker", "ConfigOption", "Dependency", "KNRM", "KNRM_class", "DRMM", "DRMM_class", "PACRR", "PACRR_class", "PTBERTMaxP", "PTBERTMaxP_Class", "DRMMTKS", "DRMMTKS_class", "ConvKNRM", "ConvKNRM_class", "CEDRKNRM", "CEDRKNRM_Class", "PTParade", "PTParade_Class"]

@@ -63,6 +63,10 @@ class BertEngine:
         self.cfg = _lib.BertConfigStruct(cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size,
                                          cfg.vocab_size, cfg.max_position_embeddings, cfg.type_vocab_size, self.n_labels,
                                          float(cfg.layer_norm_eps))
+        self._create(tensors, precision)
+        self.max_seqs_per_call = int(max_seqs_per_call)
+
+    def _create(self, tensors, precision):
         ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         handle = ctypes.c_void_p()
         lib = _lib.lib()
@@ -71,8 +75,28 @@ class BertEngine:
                                             _lib.current_stream(self.device), ctypes.byref(handle)))
             torch.cuda.current_stream(self.device).synchronize()  # the snapshot copies read `tensors`
         self.handle = handle
-        self.max_seqs_per_call = int(max_seqs_per_call)
         self._workspace = None
+
+    @classmethod
+    def from_layers(cls, bert_layers, hf_config, precision="bf16x3"):
+        """An engine made of stand-alone HF ``BertLayer`` modules (PARADE's ``transformer_layer_1/2``, ptparade.py:27-28): only its
+        encoder layers are ever run (``capr_parade_head``); the embedding / pooler / classifier slots get zeros."""
+        self = cls.__new__(cls)
+        H = hf_config.hidden_size
+        layer_tensors = []
+        for layer in bert_layers:
+            st = layer.state_dict()
+            layer_tensors += [st[k].detach().float().contiguous() for k in _LAYER_KEYS]
+        _lib.require_cuda(*layer_tensors)
+        self.device = layer_tensors[0].device
+        z = lambda *shape: torch.zeros(shape, device=self.device)
+        tensors = [z(2, H), z(2, H), z(2, H), z(H), z(H)] + layer_tensors + [z(H, H), z(H), z(2, H), z(2)]
+        self.headless, self.hidden_size, self.n_layers, self.n_labels = True, H, len(bert_layers), 2
+        self.cfg = _lib.BertConfigStruct(H, len(bert_layers), hf_config.num_attention_heads, hf_config.intermediate_size, 2, 2, 2, 2,
+                                         float(hf_config.layer_norm_eps))
+        self._create(tensors, precision)
+        self.max_seqs_per_call = 0
+        return self
 
     def __del__(self):
         try:

@@ -235,6 +235,18 @@ int capr_bert_forward_hidden(capr_bert_t handle, const int64_t* ids, const int64
                              const int* hidden_layers, int n_hidden, float* hidden_out, float* logits, void* workspace,
                              size_t workspace_bytes, capr_stream_t stream);
 
+/* ---- PARADE aggregation head -----------------------------------------------------------
+ * PTParade_Class.aggregate_using_transformer + linear (capreolus/reranker/ptparade.py:55-78): the [CLS] vector of every passage
+ * (row 0 of each passage in last_hidden [B*P*L, H], from capr_bert_forward_hidden of the passage encoder) is prefixed with
+ * `initial_cls_embedding` [H], `full_position_embeddings` [(P+1), H] are added, the B sequences of P+1 vectors run through
+ * transformer_layer_1/2 WITHOUT an attention mask and score[b] = linear(out[b, 0, :]).
+ * `agg` is a capr_bert_t created from the two BertLayers' weights (layers = 2; its embedding / pooler / classifier slots
+ * are never used: pass any finite tensors of the right shapes).  aggregated [B, H] (nullable) = transformer_out_2[:, 0, :]. */
+size_t capr_parade_workspace_bytes(capr_bert_t agg, int B, int P);
+int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, int L, const float* initial_cls, const float* pos_emb,
+                     const float* lin_w, const float* lin_b, float* scores, float* aggregated, void* workspace, size_t workspace_bytes,
+                     capr_stream_t stream);
+
 /* ---- CEDR-KNRM head ------------------------------------------------------------------
  * CEDRKNRM_Class.masked_simmats / knrm / forward (capreolus/reranker/CEDRKNRM.py:85-171) on the hidden states
  * capr_bert_forward_hidden produced for n_seq = B*P passages ([CLS] q [SEP] doc [SEP] pad; P passages per document):

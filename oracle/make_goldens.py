@@ -350,6 +350,48 @@ def make_cedrknrm():
         print("cedrknrm", name, out["default/scores"][:3].tolist())
 
 
+PARADE_CONFIGS = {
+    # name: (BertConfig kwargs, N docs, P passages, L, maxqlen, weight seed, input seed)
+    "tiny": (dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, vocab_size=1000, max_position_embeddings=64),
+             6, 3, 48, 6, 0, 23),
+    # head dim 64 (the tensor-core attention path, also for the P+1 = 5-vector aggregator sequences); small enough to commit
+    "mid": (dict(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, vocab_size=5000, max_position_embeddings=512,
+                 initializer_range=0.08), 5, 4, 200, 16, 0, 25),
+}
+
+
+def make_parade():
+    """the reference PTParade wrapper driving a seeded random-init HF BertModel.  (No BERT-base fixture:
+    the two aggregation BertLayers alone are 14 M parameters that cannot be re-derived from a seed independently of torch's
+    module-construction order; the BERT-base passage encoder itself is covered by the bert_base / cedrknrm_base goldens.)"""
+    mod = refshim.load_parade()
+    for name, (cfg, N, P, L, maxqlen, wseed, iseed) in PARADE_CONFIGS.items():
+        import transformers
+
+        vocab = transformers.BertConfig(**cfg).vocab_size
+        batch = synthetic.cedr_batch(N, P, L, maxqlen, vocab=vocab, seed=iseed)
+        tb = _t(batch)
+        out = {k: v.astype(np.int32) for k, v in batch.items()}
+        out.update(reference_commit=np.array(refshim.REFERENCE_COMMIT), weight_seed=np.array(wseed), input_seed=np.array(iseed),
+                   shape=np.array([N, P, L, maxqlen]))
+        ext = refshim.FakeExtractor(None, numpassages=P, maxseqlen=L, maxqlen=maxqlen)
+        with refshim.patched_bertmodel_from_pretrained(cfg, seed=wseed):
+            rr = mod.PTParade(dict(pretrained="bert-base-uncased", aggregation="transformer"), provide={"extractor": ext})
+            model = rr.build_model().eval()
+        with torch.no_grad():
+            model.linear.weight.mul_(4.0)
+            out["scores"] = rr.test(tb).numpy()
+            flat = lambda t: t.reshape(N * P, L)
+            cls = model.bert(flat(tb["pos_bert_input"]), attention_mask=flat(tb["pos_mask"]), token_type_ids=flat(tb["pos_seg"]))[0][:, 0, :]
+            out["cls"] = cls.numpy()
+            out["aggregated"] = model.aggregation(cls).numpy()
+        out["weight_checksum"] = bert_weight_checksum(model.bert)
+        out["config_json"] = np.array(model.bert.config.to_json_string())
+        out.update(_state_np(model, skip=("bert.",)))
+        np.savez_compressed(GOLDEN / f"parade_{name}.npz", **out)
+        print("parade", name, out["scores"][:3].tolist())
+
+
 TRAIN = dict(batch=32, itersize=512, niters=2, lr=1e-3, seed=4)
 
 
@@ -420,7 +462,7 @@ def make_losses():
                         hinge=ref.common.pair_hinge_loss([tp, tn]).numpy(), softmax=ref.common.pair_softmax_loss([tp, tn]).numpy())
 
 
-ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "drmmtks": make_drmmtks, "convknrm": make_convknrm, "cedrknrm": make_cedrknrm, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
+ALL = {"knrm": make_knrm, "drmm": make_drmm, "pacrr": make_pacrr, "drmmtks": make_drmmtks, "convknrm": make_convknrm, "cedrknrm": make_cedrknrm, "parade": make_parade, "bert": make_bert, "train": make_knrm_train, "losses": make_losses}
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)

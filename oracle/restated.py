@@ -296,6 +296,27 @@ def pair_softmax_loss(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
 # BERT math (modeling_bert.py: embeddings -> 12 x {self-attention, output LN, erf-GELU FFN, output LN}
 # -> pooler tanh -> classifier).  This is a restatement of that published algorithm; it is pinned
 # against the installed HF implementation in tests/test_oracle.py.
+def bert_layer(state: dict, p: str, x, num_heads: int, key_bias=None, eps: float = 1e-12):
+    """One HF ``BertLayer`` (self-attention + output, intermediate + output) in eval mode; ``p`` = key prefix of the layer."""
+    N, L, H = x.shape
+    dh = H // num_heads
+    g = lambda k: state[p + k]
+    split = lambda t: t.reshape(N, L, num_heads, dh).transpose(1, 2)
+    qh = split(F.linear(x, g("attention.self.query.weight"), g("attention.self.query.bias")))
+    kh = split(F.linear(x, g("attention.self.key.weight"), g("attention.self.key.bias")))
+    vh = split(F.linear(x, g("attention.self.value.weight"), g("attention.self.value.bias")))
+    logits = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    if key_bias is not None:
+        logits = logits + key_bias
+    att = torch.softmax(logits, dim=-1)
+    ctx = (att @ vh).transpose(1, 2).reshape(N, L, H)
+    y = F.linear(ctx, g("attention.output.dense.weight"), g("attention.output.dense.bias"))
+    x = F.layer_norm(x + y, (H,), g("attention.output.LayerNorm.weight"), g("attention.output.LayerNorm.bias"), eps)
+    y = F.gelu(F.linear(x, g("intermediate.dense.weight"), g("intermediate.dense.bias")))  # erf GELU
+    y = F.linear(y, g("output.dense.weight"), g("output.dense.bias"))
+    return F.layer_norm(x + y, (H,), g("output.LayerNorm.weight"), g("output.LayerNorm.bias"), eps)
+
+
 def bert_hidden_states(state: dict, ids, mask, seg, num_heads: int, eps: float = 1e-12, prefix: str = "bert.") -> list:
     """HF BertModel ``hidden_states`` (embedding output + one entry per encoder layer), eval mode.
 
@@ -314,18 +335,7 @@ def bert_hidden_states(state: dict, ids, mask, seg, num_heads: int, eps: float =
     lp = prefix + "encoder.layer."
     n_layers = 1 + max(int(k[len(lp):].split(".")[0]) for k in state if k.startswith(lp))
     for i in range(n_layers):
-        p = f"encoder.layer.{i}."
-        split = lambda t: t.reshape(N, L, num_heads, dh).transpose(1, 2)
-        qh = split(F.linear(x, g(p + "attention.self.query.weight"), g(p + "attention.self.query.bias")))
-        kh = split(F.linear(x, g(p + "attention.self.key.weight"), g(p + "attention.self.key.bias")))
-        vh = split(F.linear(x, g(p + "attention.self.value.weight"), g(p + "attention.self.value.bias")))
-        att = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh) + key_bias, dim=-1)
-        ctx = (att @ vh).transpose(1, 2).reshape(N, L, H)
-        y = F.linear(ctx, g(p + "attention.output.dense.weight"), g(p + "attention.output.dense.bias"))
-        x = F.layer_norm(x + y, (H,), g(p + "attention.output.LayerNorm.weight"), g(p + "attention.output.LayerNorm.bias"), eps)
-        y = F.gelu(F.linear(x, g(p + "intermediate.dense.weight"), g(p + "intermediate.dense.bias")))  # erf GELU
-        y = F.linear(y, g(p + "output.dense.weight"), g(p + "output.dense.bias"))
-        x = F.layer_norm(x + y, (H,), g(p + "output.LayerNorm.weight"), g(p + "output.LayerNorm.bias"), eps)
+        x = bert_layer(state, f"{prefix}encoder.layer.{i}.", x, num_heads, key_bias, eps)
         hidden.append(x)
     return hidden
 
@@ -393,6 +403,29 @@ def cedrknrm_forward(state: dict, bert_input, bert_mask, bert_seg, num_heads: in
     if combine_hidden:
         x = F.linear(x, state["combine.1.weight"], state["combine.1.bias"])
     return x
+
+
+# --------------------------------------------------------------------------------------------------
+# PARADE   (reranker/ptparade.py:55-78)   -- SURVEY.md §8(f) rank 2
+# --------------------------------------------------------------------------------------------------
+def parade_aggregate(state: dict, cls, batch_size: int, num_passages: int, num_heads: int, eps: float = 1e-12) -> torch.Tensor:
+    """``aggregate_using_transformer`` (ptparade.py:55-68): ``cls [B*P, H]`` -> ``transformer_out_2[:, 0, :]`` ``[B, H]``."""
+    H = cls.shape[-1]
+    expanded = cls.view(batch_size, num_passages, H)
+    tiled = state["initial_cls_embedding"].repeat(batch_size, 1).view(batch_size, 1, H)
+    merged = torch.cat((tiled, expanded), dim=1) + state["full_position_embeddings"]
+    out = bert_layer(state, "transformer_layer_1.", merged, num_heads, None, eps)
+    out = bert_layer(state, "transformer_layer_2.", out, num_heads, None, eps)
+    return out[:, 0, :]
+
+
+def parade_forward(state: dict, doc_input, doc_mask, doc_seg, num_heads: int, eps: float = 1e-12) -> torch.Tensor:
+    """``PTParade_Class.forward`` (ptparade.py:70-78) -> ``[B,1]``; inputs ``[B,P,L]`` int64; ``state`` = the module's state_dict."""
+    B, P, L = doc_input.shape
+    flat = lambda t: t.reshape(B * P, L)
+    cls = bert_hidden_states(state, flat(doc_input), flat(doc_mask), flat(doc_seg), num_heads, eps)[-1][:, 0, :]
+    agg = parade_aggregate(state, cls, B, P, num_heads, eps)
+    return F.linear(agg, state["linear.weight"], state["linear.bias"])
 
 
 def bert_maxp_aggregate(passage_scores, doc_mask, doc_seg, aggregation="max") -> torch.Tensor:

@@ -193,3 +193,43 @@ def test_cedrknrm_doc_chunking_is_invisible():
     model.train()
     with pytest.raises(NotImplementedError):
         rr.test(b)
+
+
+# ---- PARADE --------------------------------------------------------------------------------------
+def _build_parade(name):
+    import json
+
+    from capreolus_b200 import reranker as R
+
+    g = load_golden(f"parade_{name}")
+    cfg = json.loads(str(g["config_json"]))
+    N, P, L, maxqlen = (int(x) for x in g["shape"])
+    keep = ("hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size", "vocab_size", "max_position_embeddings",
+            "type_vocab_size", "initializer_range", "layer_norm_eps", "hidden_act")
+    torch.manual_seed(int(g["weight_seed"]))
+    rr = R.PTParade(dict(pretrained={k: cfg[k] for k in keep if k in cfg}), provide={"extractor": BertExtractor(P, L, maxqlen)})
+    model = rr.build_model()
+    tot = sum(float(v.double().abs().sum()) for v in model.bert.state_dict().values() if v.dtype.is_floating_point)
+    np.testing.assert_allclose(tot, g["weight_checksum"][0], rtol=1e-9)  # same random-init passage encoder as the golden's
+    state = {k[len("state/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state/")}
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    assert not unexpected and all(k.startswith("bert.") for k in missing), (missing, unexpected)
+    model.to(DEV).eval()
+    batch = {k: torch.from_numpy(g[k].astype(np.int64)).to(DEV) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+    return g, rr, model, batch
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_parade_matches_reference(name):
+    g, rr, model, b = _build_parade(name)
+    agg = model.aggregate_using_transformer_output(b["pos_bert_input"], b["pos_mask"], b["pos_seg"]).cpu().numpy()
+    np.testing.assert_allclose(agg, g["aggregated"], atol=2e-3)  # LayerNorm outputs, |x| ~ 1
+    scores = rr.test(b).cpu().numpy()
+    assert scores.shape == g["scores"].shape
+    assert rel_err(scores, g["scores"], floor=1e-2) < TOL
+    # chunking over documents is invisible
+    model.max_seqs_per_call, model._engine = int(g["shape"][1]), None
+    assert torch.equal(rr.test(b).cpu(), torch.from_numpy(scores))
+    model.train()
+    with pytest.raises(NotImplementedError):
+        rr.test(b)

@@ -233,3 +233,21 @@ def test_cedrknrm_scores(name):
             got = restated.cedrknrm_forward(state, tb["pos_bert_input"], tb["pos_mask"], tb["pos_seg"], cfg["num_attention_heads"], maxqlen,
                                             vcfg["simmat_layers"], vcfg["cls"], vcfg["combine_hidden"]).view(-1).numpy()
         assert rel_err(got, g[f"{variant}/scores"], floor=1e-2) < 1e-4, variant
+
+
+# ---- PARADE ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_parade_scores(name):
+    g = load_golden(f"parade_{name}")
+    N, P, L, maxqlen = (int(x) for x in g["shape"])
+    tb = {k: torch.from_numpy(g[k].astype(np.int64)) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+    state, cfg = _cedr_state(g, "")  # encoder re-derived from its seed + the stored aggregator / linear parameters
+    state.update({k[len("state/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state/")})
+    nh = cfg["num_attention_heads"]
+    with torch.no_grad():
+        flat = lambda t: t.reshape(N * P, L)
+        cls = restated.bert_hidden_states(state, flat(tb["pos_bert_input"]), flat(tb["pos_mask"]), flat(tb["pos_seg"]), nh)[-1][:, 0, :]
+        np.testing.assert_allclose(cls.numpy(), g["cls"], atol=2e-5)
+        np.testing.assert_allclose(restated.parade_aggregate(state, cls, N, P, nh).numpy(), g["aggregated"], atol=2e-5)
+        got = restated.parade_forward(state, tb["pos_bert_input"], tb["pos_mask"], tb["pos_seg"], nh).view(-1).numpy()
+    assert rel_err(got, g["scores"], floor=1e-2) < 1e-4
