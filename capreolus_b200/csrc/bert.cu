@@ -19,6 +19,7 @@
 
 #include "bert_attn.cuh"
 #include "bert_attn2.cuh"
+#include "bert_gemm2.cuh"
 #include "tmap.cuh"
 
 namespace capr {
@@ -319,6 +320,8 @@ struct Linear {  // one nn.Linear prepared for the tensor cores
   __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
   float* bias = nullptr;
   CUtensorMap map_hi, map_lo;
+  bool has_pair_maps = false;      // N % 256 == 0: {64, 128} boxes for the CTA-pair kernel (each CTA loads half of the B tile)
+  CUtensorMap pair_hi, pair_lo;
 };
 
 struct Layer {
@@ -336,6 +339,8 @@ struct Model {
   int sms = 0;
   bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
   bool attention_v1 = false;    // CAPR_BERT_ATTENTION=v1: the first tensor-core attention (128 queries per CTA), for A/B tests
+  bool gemm_pairs = true;       // CAPR_BERT_GEMM=1cta: force the one-CTA GEMM (A/B tests)
+  int max_pairs = 0;            // co-resident CTA pairs of gemm2_kernel (cudaOccupancyMaxActiveClusters)
 };
 
 static int dev_alloc(Model* m, void** p, size_t bytes) {
@@ -372,13 +377,53 @@ static int make_linear(Model* m, Linear* lin, int K, const float* const* ws, con
   }
   if ((rc = make_map(&lin->map_hi, lin->w_hi, N, K, lin->BN))) return rc;
   if ((rc = make_map(&lin->map_lo, lin->w_lo, N, K, lin->BN))) return rc;
+  if (N % G2_BN == 0) {
+    if ((rc = make_map(&lin->pair_hi, lin->w_hi, N, K, G2_BN / 2))) return rc;
+    if ((rc = make_map(&lin->pair_lo, lin->w_lo, N, K, G2_BN / 2))) return rc;
+    lin->has_pair_maps = true;
+  }
   return CAPR_OK;
+}
+
+// Co-resident clusters of gemm2_kernel<MODE> (the persistent grid must not exceed it: tiles are statically partitioned).
+template <int MODE>
+static int pair_capacity(int sms) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  if (cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<MODE>::BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(sms & ~1), 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Gemm2Smem<MODE>::BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<MODE>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached = n;
 }
 
 template <int MODE>
 static int launch_gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const Linear& lin, int M, int epi, const float* resid,
                        float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
   GemmArgs g{M, lin.N, lin.K, lin.BN, epi, lin.bias, resid, out_f32, out_hi, out_lo};
+  if (m->gemm_pairs && lin.has_pair_maps && M > BM) {
+    const int cap = pair_capacity<MODE>(m->sms);
+    if (cap > 0) {
+      const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (lin.N / G2_BN);
+      const int pairs = pair_tiles < cap ? pair_tiles : cap;
+      gemm2_kernel<MODE><<<2 * pairs, GEMM_THREADS, Gemm2Smem<MODE>::BYTES, st>>>(a_hi, a_lo, lin.pair_hi, lin.pair_lo, g);
+      CAPR_CHECK_CUDA(cudaGetLastError());
+      return CAPR_OK;
+    }
+  }
   const int tiles = ((M + BM - 1) / BM) * (lin.N / lin.BN);
   const int grid = tiles < m->sms ? tiles : m->sms;
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<MODE>::BYTES));
@@ -456,6 +501,8 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
     const char* e = getenv("CAPR_BERT_ATTENTION");
     m->ffma_attention = e && e[0] == 'f';
     m->attention_v1 = e && e[0] == 'v' && e[1] == '1';
+    const char* ge = getenv("CAPR_BERT_GEMM");
+    m->gemm_pairs = !(ge && ge[0] == '1');
   }
   const size_t H = cfg->hidden, I = cfg->intermediate;
   int rc = CAPR_OK;
