@@ -38,7 +38,7 @@ ENCODERS = ("bert", "cedrknrm")  # models whose hot path is the BERT encoder (te
 BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
 MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM"}
 DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512}
-DEFAULT_CHUNK = {"knrm": 12_500, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500, "cedrknrm": 128}
+DEFAULT_CHUNK = {"knrm": 6_250, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500, "cedrknrm": 128}
 TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)",
               "cedrknrm": "gemm_kernel<3> (+ attention_tc2_kernel, cedr_pool_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
