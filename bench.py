@@ -292,7 +292,8 @@ def main():
         sampler.stop_flag = True
         e2e_ms = e0.elapsed_time(e1)
         mine = scores[rank * n:(rank + 1) * n] if world > 1 else scores
-        assert torch.equal(out.to(dev), mine), "pipelined predict != direct test"
+        check = not os.environ.get("CAPR_BENCH_NOCHECK")  # profiling runs with CAPR_*_DEBUG switches produce invalid scores
+        assert not check or torch.equal(out.to(dev), mine), "pipelined predict != direct test"
         # ---- end to end from a packed, device-resident id store: only (query, doc) indices cross PCIe ----
         packed_ms = None
         if args.model not in ENCODERS:
@@ -318,7 +319,7 @@ def main():
             p1.record()
             barrier()
             packed_ms = p0.elapsed_time(p1)
-            assert torch.equal(host_scores.to(dev), mine), "packed-store predict != direct test"
+            assert not check or torch.equal(host_scores.to(dev), mine), "packed-store predict != direct test"
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms, packed_ms or 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

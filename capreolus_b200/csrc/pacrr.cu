@@ -39,6 +39,8 @@ struct PacrrArgs {
   float* scores;
   float* topk_out;
   simtc::Problem pr;  // tensor-core engine only
+  const float* conv_w[MAX_GRAMS];  // device pointers (conv-on-tensor-cores epilogue builds its filter tile from them)
+  const float* conv_b[MAX_GRAMS];
 };
 
 struct BlockSync {
@@ -162,6 +164,9 @@ __device__ __forceinline__ void ngram_dispatch(int n, const float* s, const Pacr
   else ngram_dispatch_n<FT, MAX_KMAX>(n, s, a, feat, qterm, col0, warp, lane);
 }
 
+template <class Sync>
+__device__ __forceinline__ void pacrr_tail(const PacrrArgs& a, int pair, float* feat, float* h1, float* h2, int tid, Sync sync);
+
 // Everything after the cosine tile: n-gram conv/max/top-k passes, softmax(idf) channel, 3-layer combine MLP.
 // Runs on 8 warps (tid 0..255); `sync` is the barrier of exactly those warps.
 template <class Sync>
@@ -175,6 +180,15 @@ __device__ __forceinline__ void pacrr_epilogue(const float* sim, const PacrrArgs
     if (a.F == 32) ngram_dispatch<32>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
     else ngram_dispatch<0>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
   }
+  pacrr_tail(a, pair, feat, h1, h2, tid, sync);
+}
+
+// softmax(idf) channel + 3-layer combine MLP on the [Q][qterm] feature block (8 warps, tid 0..255).
+template <class Sync>
+__device__ __forceinline__ void pacrr_tail(const PacrrArgs& a, int pair, float* feat, float* h1, float* h2, int tid, Sync sync) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ngrams = a.maxgram - a.mingram + 1;
+  const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
   if (a.idf && warp == 0) {
     // softmax over the query axis of the raw idf vector, pads included (PACRR.py:47-50)
     const float v = lane < a.Q ? a.idf[(size_t)pair * a.Q + lane] : -INFINITY;
@@ -258,6 +272,236 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   teardown(s, tmem_base, tid);
 }
 
+// ---- Engine 3: the convolutions on tensor cores too --------------------------------------------------------------------
+// relu(max_f(b_f + sum_taps w_f[tap] * S[i+u][j+v])) for the 1x1, 2x2 and 3x3 windows is ONE skinny GEMM per block of 128
+// cells: A = im2col rows of the 3x3 window (the smaller windows are its top-left corners: zero weights elsewhere), B = the
+// 3 x 32 filters, bias folded in as two constant-one K columns.  fp32 accuracy comes from the same split as everywhere
+// else: every cosine S and every weight W is (hi, lo) bf16 and the K axis carries S_hi*W_hi + S_lo*W_hi + S_hi*W_lo per
+// tap -> K = 9 taps x 3 + 2 bias = 29 <= 32, i.e. two tcgen05.mma (M=128, N=32*ngrams, K=16) per 128 cells instead of
+// 448 FMAs per cell.  The 8 epilogue warps build the A tile (no-swizzle K-major core-matrix layout, 16-byte stores),
+// one elected thread issues the MMAs, and while they run the same warps reduce the PREVIOUS block: tcgen05.ld of its
+// [128 x 32*ngrams] accumulator, max over the 32 filters of each window size, ReLU, lane-local running top-k of the row;
+// at the end of each query row the 256 lane-local lists are merged through shared memory.
+// STATUS: parity-green, opt-in (CAPR_PACRR_CONV=tc3), NOT the default: measured 1.1 M pairs/s against 2.5 M for the FFMA2
+// epilogue -- see the note in pacrr_run and DESIGN.md.
+// Resources: the cosine-tile producer runs in `single` mode (one query buffer, one TMEM accumulator buffer), which
+// frees shared memory for two 8 KB A stages + the 6 KB filter tile + the merge scratch, and TMEM columns 256-511 for
+// two conv accumulators.  Used when nfilters == 32, maxgram <= 3, kmax <= 4 (the reference defaults); other configs
+// keep the FFMA2 epilogue above.
+constexpr int C3_A_STAGE = 128 * 64;            // 128 cells x 32 bf16
+constexpr int C3_B_BYTES = 96 * 64;             // up to 96 filter columns x 32 bf16
+constexpr int C3_KM = 4;                        // kmax limit of this path
+constexpr int C3_SCRATCH = 3 * 256 * C3_KM * 4; // merge scratch: [ngram][thread][k]
+constexpr int C3_BYTES = 2 * C3_A_STAGE + C3_B_BYTES + C3_SCRATCH;  // 34 816 B
+
+__device__ __forceinline__ uint32_t c3_off(int row, int chunk) { return (uint32_t)((row >> 3) * 512 + chunk * 128 + (row & 7) * 16); }
+
+__device__ __forceinline__ void c3_split(float x, uint32_t& h, uint32_t& l) {
+  const __nv_bfloat16 hb = __float2bfloat16_rn(x);
+  h = (uint32_t)__bfloat16_as_ushort(hb);
+  l = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(hb)));
+}
+
+template <int KM>
+__device__ __forceinline__ void c3_insert(float (&top)[KM], float v) {
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    if (v > top[k]) {
+      const float t = top[k];
+      top[k] = v;
+      v = t;
+    }
+  }
+}
+
+template <int KM>
+__global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc3_kernel(const PacrrArgs a) {
+  using namespace simtc;
+  extern __shared__ unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int atoms = (a.pr.pitch + ATOM_K - 1) / ATOM_K;
+  Smem s = carve(smem_raw, atoms);
+  const int ngrams = a.maxgram - a.mingram + 1;
+  const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
+  float* feat = s.extra;  // [QT][qterm]
+  float* h1 = feat + QT * qterm;
+  float* h2 = h1 + MAX_COMBINE;
+  uint64_t* conv_full = reinterpret_cast<uint64_t*>(h2 + MAX_COMBINE);  // [2]
+  // conv buffers: the unused second query buffer when it is large enough, else behind the barriers in the extra region
+  unsigned char* cbuf = atoms * Q_ATOM_BYTES >= C3_BYTES ? s.qbuf(1) : reinterpret_cast<unsigned char*>(conv_full + 2);
+  cbuf += (128u - (tc::smem_u32(cbuf) & 127u)) & 127u;
+  unsigned char* a_stage = cbuf;                         // 2 x 8 KB
+  unsigned char* b_tile = cbuf + 2 * C3_A_STAGE;          // 6 KB
+  float* scratch = reinterpret_cast<float*>(b_tile + C3_B_BYTES);  // [ngram][256][KM]
+  if (tid == 0) {
+    tc::mbar_init(&conv_full[0], 1);
+    tc::mbar_init(&conv_full[1], 1);
+  }
+  const uint32_t tmem_base = setup(s, tid);  // fence.mbarrier_init + __syncthreads inside
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    producer_loop(s, a.pr, tid - EPI_THREADS);
+  } else if (warp == EPI_WARPS + PROD_WARPS) {
+    mma_loop(s, a.pr, tmem_base);
+  } else {
+    const int Ntot = ngrams * 32;
+    // ---- filter tile, once: column n = g*32 + f; K slots: taps 0-4 -> 3t+{0,1,2} = (W_hi, W_hi, W_lo), slot 15 = 0;
+    //      taps 5-8 -> 16 + 3(t-5) + {0,1,2}; slots 28, 29 = (b_hi, b_lo); 30, 31 = 0
+    for (int idx = tid; idx < Ntot * 32; idx += EPI_THREADS) {
+      const int n = idx >> 5, slot = idx & 31;
+      const int g = n >> 5, f = n & 31, win = a.mingram + g;
+      float val = 0.f;
+      int part = -1;  // 0: hi, 1: lo
+      if (slot < 15 || (slot >= 16 && slot < 28)) {
+        const int t = slot < 15 ? slot / 3 : 5 + (slot - 16) / 3;
+        const int r = slot < 15 ? slot % 3 : (slot - 16) % 3;
+        const int u = t / 3, v = t % 3;
+        if (u < win && v < win) {
+          val = a.conv_w[g][(size_t)f * win * win + u * win + v];
+          part = r == 2 ? 1 : 0;
+        }
+      } else if (slot == 28 || slot == 29) {
+        val = a.conv_b[g][f];
+        part = slot - 28;
+      }
+      uint32_t h = 0, l = 0;
+      if (part >= 0) c3_split(val, h, l);
+      *reinterpret_cast<unsigned short*>(b_tile + c3_off(n, slot >> 3) + (slot & 7) * 2) = (unsigned short)(part == 1 ? l : h);
+    }
+    tc::fence_proxy_async();
+    epi_barrier();
+    const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, 128, Ntot);
+    const uint32_t a_addr = tc::smem_u32(a_stage), b_addr = tc::smem_u32(b_tile);
+    const int grp = warp >> 2, quarter = warp & 3;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int NBJ = (a.D + 127) / 128;
+    const int NB = a.Q * NBJ;
+    uint32_t acc_phase = 0, conv_phase = 0;  // one bit per buffer
+    int unit = 0;
+    const int dbg = a.pr.debug;  // profiling only (CAPR_PACRR_DEBUG): 0x10000 no build, 0x20000 no MMA, 0x40000 no reduce, 0x80000 no fence
+    for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
+      drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);  // -> s.sim (fp32, zero halo); ends with epi_barrier
+      float top[3][KM];
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int k = 0; k < KM; ++k) top[g][k] = -INFINITY;
+      for (int b = 0; b <= ((dbg & 0x200000) ? -1 : NB); ++b) {
+        if (b < NB && !(dbg & 0x10000)) {
+          // ---- build the A tile of block b: cell = tid & 127, this thread writes K chunks 2*half, 2*half+1
+          const int i = b / NBJ, jb = b - i * NBJ;
+          const int cell = tid & 127, half = tid >> 7;
+          const float* p = s.sim + i * SIM_PITCH + jb * 128 + cell;
+          uint32_t w[8];
+          if (half == 0) {
+            uint32_t h0, l0, h1_, l1, h2_, l2, h3, l3, h4, l4;
+            c3_split(p[0], h0, l0);                      // tap (0,0)
+            c3_split(p[1], h1_, l1);                     // (0,1)
+            c3_split(p[2], h2_, l2);                     // (0,2)
+            c3_split(p[SIM_PITCH], h3, l3);              // (1,0)
+            c3_split(p[SIM_PITCH + 1], h4, l4);          // (1,1)
+            w[0] = h0 | (l0 << 16), w[1] = h0 | (h1_ << 16), w[2] = l1 | (h1_ << 16), w[3] = h2_ | (l2 << 16);
+            w[4] = h2_ | (h3 << 16), w[5] = l3 | (h3 << 16), w[6] = h4 | (l4 << 16), w[7] = h4;
+          } else {
+            uint32_t h5, l5, h6, l6, h7, l7, h8, l8;
+            c3_split(p[SIM_PITCH + 2], h5, l5);          // (1,2)
+            c3_split(p[2 * SIM_PITCH], h6, l6);          // (2,0)
+            c3_split(p[2 * SIM_PITCH + 1], h7, l7);      // (2,1)
+            c3_split(p[2 * SIM_PITCH + 2], h8, l8);      // (2,2)
+            w[0] = h5 | (l5 << 16), w[1] = h5 | (h6 << 16), w[2] = l6 | (h6 << 16), w[3] = h7 | (l7 << 16);
+            w[4] = h7 | (h8 << 16), w[5] = l8 | (h8 << 16), w[6] = 0x3F803F80u, w[7] = 0u;  // bias columns: 1.0, 1.0
+          }
+          unsigned char* st = a_stage + (b & 1) * C3_A_STAGE;
+          *reinterpret_cast<uint4*>(st + c3_off(cell, 2 * half)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(st + c3_off(cell, 2 * half + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+          if (!(dbg & 0x80000)) tc::fence_proxy_async();
+        }
+        if (!(dbg & 0x400000)) tc::tc_fence_before();  // the previous iteration's tcgen05.ld of the accumulator this block's MMAs overwrite
+        if (!(dbg & 0x800000)) epi_barrier();
+        if (b < NB && warp == 0 && !(dbg & 0x20000)) {
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
+            const uint32_t st = a_addr + (uint32_t)((b & 1) * C3_A_STAGE);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(256 + (b & 1) * 128);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              tc::umma_f16(d_tmem, tc::make_nosw_kmajor_desc(st + ks * 256, 128, 512), tc::make_nosw_kmajor_desc(b_addr + ks * 256, 128, 512),
+                           idesc, ks != 0);
+            tc::umma_commit(&conv_full[b & 1]);
+          }
+          __syncwarp();
+        }
+        if (b >= 1) {
+          // ---- reduce block b-1: max over the 32 filters of each window size, ReLU, running top-k of the row
+          const int pb = b - 1, buf = pb & 1;
+          const int i = pb / NBJ, jb = pb - i * NBJ;
+          if (!(dbg & 0x20000)) tc::mbar_wait(&conv_full[buf], (conv_phase >> buf) & 1);
+          conv_phase ^= 1u << buf;
+          if (!(dbg & 0x1000000)) tc::tc_fence_after();
+          const int j = jb * 128 + quarter * 32 + lane;
+          // which window sizes this warp group takes for this block (balanced 64 + 32 columns, alternating)
+          int g_lo, g_hi;
+          if (ngrams == 3) {
+            if (((pb ^ grp) & 1) == 0) g_lo = 0, g_hi = 2; else g_lo = 2, g_hi = 3;
+          } else {
+            g_lo = grp, g_hi = grp < ngrams ? grp + 1 : grp;
+          }
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            if (g >= g_lo && g < g_hi && !(dbg & 0x40000)) {  // warp-uniform
+              float v[32];
+              tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(256 + buf * 128 + g * 32), v);
+              tc::tmem_ld_wait();
+              float m = v[0];
+#pragma unroll
+              for (int f = 1; f < 32; ++f) m = fmaxf(m, v[f]);
+              m = j < a.D ? fmaxf(m, 0.f) : -INFINITY;  // ReLU commutes with the filter max; columns past the doc do not exist
+              c3_insert<KM>(top[g], m);
+            }
+          }
+          if (jb == NBJ - 1 && !(dbg & 0x100000)) {
+            // ---- end of query row i: merge the 256 lane-local lists of every window size
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+              for (int k = 0; k < KM; ++k) {
+                if (g < ngrams) scratch[(g * 256 + tid) * KM + k] = top[g][k];
+                top[g][k] = -INFINITY;
+              }
+            epi_barrier();
+            if (warp < ngrams) {
+              float c[8 * KM];
+#pragma unroll
+              for (int w = 0; w < 8; ++w)
+#pragma unroll
+                for (int k = 0; k < KM; ++k) c[w * KM + k] = scratch[(warp * 256 + w * 32 + lane) * KM + k];
+              for (int k = 0; k < a.kmax; ++k) {
+                float m = c[0];
+#pragma unroll
+                for (int e = 1; e < 8 * KM; ++e) m = fmaxf(m, c[e]);
+                const float M = warp_max(m);
+                const unsigned who = __ballot_sync(0xffffffffu, m == M);
+                if (lane == __ffs(who) - 1) {  // remove ONE instance of the maximum
+                  bool done = false;
+#pragma unroll
+                  for (int e = 0; e < 8 * KM; ++e) {
+                    const bool hit = !done && c[e] == M;
+                    c[e] = hit ? -INFINITY : c[e];
+                    done = done || hit;
+                  }
+                }
+                if (lane == 0) feat[i * qterm + warp * a.kmax + k] = M;
+              }
+            }
+            epi_barrier();  // scratch is rewritten at the end of the next row; feat row i is complete
+          }
+        }
+      }
+      pacrr_tail(a, pair, feat, h1, h2, tid, EpiSync());
+    }
+  }
+  teardown(s, tmem_base, tid);
+}
+
 }  // namespace capr
 
 using namespace capr;
@@ -293,6 +537,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
     const int n = mingram + g;
     CAPR_REQUIRE(conv_w[g] && conv_b[g], CAPR_ERR_BAD_POINTER, "%s: null conv weight %d", fn, g);
     a.w_off[g] = conv_w_slot(n);
+    a.conv_w[g] = conv_w[g], a.conv_b[g] = conv_b[g];
     CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_w, conv_w[g], sizeof(float) * nfilters * n * n, sizeof(float) * conv_w_slot(n), cudaMemcpyDeviceToDevice, st));
     CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_conv_b, conv_b[g], sizeof(float) * nfilters, sizeof(float) * conv_b_slot(n), cudaMemcpyDeviceToDevice, st));
   }
@@ -300,7 +545,27 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   const size_t extra_tc = (size_t)(QT * ((maxgram - mingram + 1) * kmax + (idf ? 1 : 0)) + 2 * MAX_COMBINE) * sizeof(float);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
-  if (tc_engine) {
+  // CAPR_PACRR_CONV=tc3 selects the experimental conv-on-tensor-cores epilogue (engine 3).  It is parity-green but measured
+  // SLOWER than the FFMA2 epilogue (1.1 M vs 2.5 M pairs/s): the im2col build + TMEM reduce + top-k cost ~430 dependent
+  // thread-instructions per cell on 8 warps (ncu source view), no fewer than the 350 high-ILP FFMA2 / FMNMX of the default path.
+  const char* conv_env = getenv("CAPR_PACRR_CONV");
+  if (tc_engine && nfilters == 32 && maxgram <= 3 && kmax <= C3_KM && conv_env && conv_env[0] == 't') {
+    // engine 3: convolutions on tensor cores as well
+    const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
+    const size_t conv_extra = (size_t)atoms * simtc::Q_ATOM_BYTES >= (size_t)C3_BYTES ? 0 : (size_t)C3_BYTES + 128;
+    const size_t smem = simtc::smem_bytes(atoms, extra_tc + 2 * sizeof(uint64_t) + 8 + conv_extra);
+    CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: shared memory budget exceeded", fn);
+    CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit row offsets", fn);
+    a.pr.single = 1;
+    if (const char* de = getenv("CAPR_PACRR_DEBUG")) a.pr.debug = (int)strtol(de, nullptr, 0) & 0x1FF0000;
+    if (kmax <= 2) {
+      CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pacrr_tc3_kernel<2><<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+    } else {
+      CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc3_kernel<C3_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pacrr_tc3_kernel<C3_KM><<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+    }
+  } else if (tc_engine) {
     const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, extra_tc);
     CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: ngrams*kmax too large for the tensor-core engine's shared memory: use capr_pacrr_forward", fn);
     CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit row offsets", fn);

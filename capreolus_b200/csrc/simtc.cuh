@@ -10,9 +10,9 @@
 //     64-127 read whatever follows in shared memory and produce accumulator rows nobody reads), 256 DOC rows are the N
 //     operand.  Per K step two MMAs: B = d_hi gives rows 0-31 = q_hi.d_hi and rows 32-63 = q_lo.d_hi, B = d_lo adds
 //     q_hi.d_lo to rows 0-31 (and the negligible q_lo.d_lo to rows 32-63).  cos[i][d] = D[i][d] + D[32+i][d].
-//     (A tcgen05.mma with shared-memory operands costs >= ~128 cycles whatever N is -- measured -- so the first
-//     orientation of this kernel, docs as M=128 and the query block as N=64/32, needed 152 MMAs per pair and was
-//     MMA-chain bound at 11 M pairs/s; N=256 needs 76.)  CPU emulation of the three-product arithmetic against the
+//     (The first orientation of this kernel, docs as M=128 and the query block as N=64/32, needed 152 MMAs per pair at
+//     ~61 cycles each -- a tcgen05.mma costs max(~60, N/2) cycles, scripts/mma_bench.py -- and was MMA-chain bound at
+//     11 M pairs/s; N=256 needs 76 MMAs of 128 cycles that run the pipe at its full rate.)  CPU emulation of the three-product arithmetic against the
 //     goldens: KNRM 8e-7, PACRR 2e-5, DRMM 0 bin flips (tests/emulate.py);
 //   * rows are gathered with 16-byte cp.async straight into the canonical SWIZZLE_128B K-major layout (8 lanes fetch
 //     one 128-byte row segment: fully coalesced) and completed on mbarriers with cp.async.mbarrier.arrive.noinc, so
@@ -114,6 +114,8 @@ struct Problem {
   int pitch;                // elements per table row, multiple of 16 (the last 64-element K atom may be partial)
   int E;
   int debug;                // CAPR_DEBUG_* profiling switches (0 in production)
+  int single;               // 1: use only query buffer 0 and TMEM accumulator buffer 0 (PACRR's conv-on-tensor-cores epilogue
+                            // needs the second query buffer's shared memory and half of TMEM for itself)
 };
 
 __device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
@@ -174,7 +176,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   uint32_t q_phase = 0, d_phase = 0;  // q_phase: one bit per buffer
   int d_stage = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
-    const int b = it & 1;
+    const int b = pr.single ? 0 : (it & 1);
     prod_barrier();  // every producer thread is done reading the previous pair's rows
     if (ptid < QT) s.qrow[ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
     for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
@@ -234,12 +236,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   uint32_t q_phase = 0, acc_phase = 0, d_phase = 0;  // q/acc: one bit per buffer
   int d_stage = 0, it = 0, unit = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
-    const int b = it & 1;
+    const int b = pr.single ? 0 : (it & 1);
     tc::mbar_wait(&s.q_full[b], (q_phase >> b) & 1);
     q_phase ^= 1u << b;
     const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.qbuf(b)));
     for (int h = 0; h < halves; ++h, ++unit) {
-      const int ab = unit & 1;
+      const int ab = pr.single ? 0 : (unit & 1);
       tc::mbar_wait(&s.acc_empty[ab], ((acc_phase >> ab) & 1) ^ 1);
       acc_phase ^= 1u << ab;
       tc::tc_fence_after();
@@ -292,7 +294,7 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
     const uint32_t lane_off = (uint32_t)((warp & 1) * 32) << 16;
     const int qi = s.qid[lane];
     for (int h = 0; h < halves; ++h) {
-      const int ab = (first_unit + h) & 1;
+      const int ab = pr.single ? 0 : ((first_unit + h) & 1);
       tc::mbar_wait(&s.acc_full[ab], (acc_phase >> ab) & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -332,7 +334,7 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
       acc_phase ^= 1u << ab;
     }
   } else {
-    for (int h = 0; h < halves; ++h) acc_phase ^= 1u << ((first_unit + h) & 1);  // same phase bookkeeping in every warp
+    for (int h = 0; h < halves; ++h) acc_phase ^= 1u << (pr.single ? 0 : ((first_unit + h) & 1));  // same phase bookkeeping in every warp
   }
   epi_barrier();
 }

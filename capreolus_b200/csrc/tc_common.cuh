@@ -40,15 +40,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp instead of having it spin: without it the producer / MMA
+// warps of the persistent kernels burned a third of the issue slots in try_wait loops (ncu source view of pacrr_tc3_kernel:
+// 290 k of 897 k stall samples sat on two spin branches executed 300 M times).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 
@@ -149,6 +152,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+// K-major operand tile WITHOUT swizzle (canonical "interleaved" layout ((8,m),(8,2k)):((16 B, SBO),(1, LBO)) for 16-bit types):
+// core matrices of 8 rows x 16 bytes are contiguous (128 B); `lbo` = bytes between core matrices adjacent in K, `sbo` = bytes
+// between 8-row groups.  16-byte alignment is enough.
+__device__ __forceinline__ uint64_t make_nosw_kmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); layout bits [61,64) = 0: no swizzle
   return d;
 }
 

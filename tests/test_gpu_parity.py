@@ -279,3 +279,21 @@ def test_full_size_properties(engine):
         idx = torch.arange(0, N, N // 48)[:48]
         want = restated.knrm_forward(state, torch.from_numpy(table), gpu["posdoc"][idx].cpu(), gpu["query"][idx].cpu()).view(-1).numpy()
     assert rel_err(s[idx].cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pacrr_conv_on_tensor_cores_engine_matches_reference(shape, monkeypatch):
+    """The opt-in engine 3 (CAPR_PACRR_CONV=tc3: im2col + tcgen05 conv) computes the same scores and top-k."""
+    monkeypatch.setenv("CAPR_PACRR_CONV", "tc3")
+    g = load_golden(f"pacrr_{shape}")
+    for variant in ("default", "noidf_tanh"):
+        rr, model = _build("PACRR", g, variant, PACRR_CFG[variant])
+        b = _batch(g)
+        with torch.no_grad():
+            pos, neg = rr.score(b)
+        assert rel_err(pos.cpu().numpy(), g[f"{variant}/pos"]) < TOL
+        assert rel_err(neg.cpu().numpy(), g[f"{variant}/neg"]) < TOL
+    rr, model = _build("PACRR", g, "default", PACRR_CFG["default"])
+    with torch.no_grad():
+        topk = model.ngram_topk(_batch(g)["posdoc"], _batch(g)["query"]).cpu().numpy()
+    np.testing.assert_allclose(topk, g["topk"], rtol=1e-4, atol=2e-5)
