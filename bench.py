@@ -33,14 +33,15 @@ Q, D, V, E = synthetic.MAXQLEN, synthetic.MAXDOCLEN, synthetic.VOCAB, synthetic.
 # ids (32+512)*8 B + gathered rows 544*300*4 B + one fp32 score
 ALGO_BYTES_PER_PAIR = (Q + D) * 8 + (Q + D) * E * 4 + 4
 BERT_L = 512
-ENCODERS = ("bert", "cedrknrm")  # models whose hot path is the BERT encoder (tensor-pipe roofline)
+ENCODERS = ("bert", "cedrknrm", "parade")  # models whose hot path is the BERT encoder (tensor-pipe roofline)
+PARADE_P, PARADE_L = 4, 163  # PARADE: the 512-token document as 4 passages of 128 tokens: [CLS] q(32) [SEP] passage(128) [SEP]
 # per layer 2*12*768^2*512 (Linear layers) + 2*2*512^2*768 (attention) = 8.05 GFLOP; x12 layers = 96.6 GFLOP
 BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
-MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM"}
-DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512}
-DEFAULT_CHUNK = {"knrm": 6_250, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500, "cedrknrm": 128}
-TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm_kernel<3> (+ attention_tc_kernel)",
-              "cedrknrm": "gemm_kernel<3> (+ attention_tc2_kernel, cedr_pool_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
+MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM", "parade": "PTParade"}
+DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512, "parade": 1024}
+DEFAULT_CHUNK = {"knrm": 6_250, "drmm": 12_500, "pacrr": 12_500, "bert": 256, "drmmtks": 12_500, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
+TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm2_kernel<3> (+ attention_tc2_kernel)",
+              "cedrknrm": "gemm2_kernel<3> (+ attention_tc2_kernel, cedr_pool_kernel)", "parade": "gemm2_kernel<3> (+ attention_tc2_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
 
 
@@ -100,7 +101,9 @@ def build_reranker(model_key):
     from capreolus_b200 import reranker as R
 
     torch.manual_seed(0)
-    if model_key == "cedrknrm":
+    if model_key == "parade":
+        rr = R.PTParade(dict(pretrained={}), provide={"extractor": Extractor(numpassages=PARADE_P, maxseqlen=PARADE_L, maxqlen=Q)})
+    elif model_key == "cedrknrm":
         rr = R.CEDRKNRM(dict(pretrained={}, simmat_layers="0..12,1", cls="avg"), provide={"extractor": Extractor(numpassages=1, maxseqlen=BERT_L, maxqlen=Q)})
     elif model_key == "bert":
         rr = R.PTBERTMaxP(dict(pretrained={}, aggregation="max", hidden_dropout_prob=0.1), provide={"extractor": Extractor(numpassages=1, maxseqlen=BERT_L)})
@@ -110,7 +113,9 @@ def build_reranker(model_key):
 
 
 def host_batch(model_key, n, seed):
-    if model_key in ENCODERS:
+    if model_key == "parade":
+        b = synthetic.bert_batch(n, seqlen=PARADE_L, qlen=Q, seed=seed, numpassages=PARADE_P, ragged=False)
+    elif model_key in ENCODERS:
         b = synthetic.bert_batch(n, seqlen=BERT_L, qlen=Q, seed=seed, numpassages=1, ragged=False)
     else:
         b = synthetic.throughput_batch(n, Q, D, V, seed=seed)
@@ -127,6 +132,15 @@ def cpu_reference_step(model_key, state):
     from oracle import restated
 
     torch.set_num_threads(os.cpu_count() or 1)
+    if model_key == "parade":
+        b = host_batch("parade", 4, seed=3)
+
+        def step():
+            with torch.no_grad():
+                restated.parade_forward(state, b["pos_bert_input"], b["pos_mask"], b["pos_seg"], 12)
+            return 4
+
+        return step, f"oracle/restated.parade_forward (reference op sequence: BERT-base over {PARADE_P} passages of L={PARADE_L} + 2 aggregation BertLayers), B=4"
     if model_key == "cedrknrm":
         b = host_batch("cedrknrm", 4, seed=3)
 
@@ -329,15 +343,22 @@ def main():
     if rank == 0:
         pk = peaks()
         if args.model in ENCODERS:
-            achieved = BERT_FLOPS_PER_PAIR * n / (kernel_ms * 1e-3) / 1e12
+            flops_pair = BERT_FLOPS_PER_PAIR
+            if args.model == "parade":  # P passages of PARADE_L tokens (the 2 aggregation layers over P+1 vectors are < 0.1 %)
+                flops_pair = PARADE_P * 12 * (2 * 12 * 768 * 768 * PARADE_L + 2 * 2 * PARADE_L * PARADE_L * 768)
+            achieved = flops_pair * n / (kernel_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
                     "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)", "kernel": TOP_KERNEL[args.model],
-                    "algorithmic_flops_per_pair": BERT_FLOPS_PER_PAIR, "issued_tensor_flops_per_pair": 3 * BERT_FLOPS_PER_PAIR,
+                    "algorithmic_flops_per_pair": flops_pair, "issued_tensor_flops_per_pair": 3 * flops_pair,
                     "note": "achieved counts ALGORITHMIC flops over the whole forward; the bf16x3 parity mode issues 3 tensor-core products per "
                             "algorithmic flop (Linear layers and attention)", "forward_ms": kernel_ms, "pairs_per_forward": n}
-            launches = args.steps * ((2 + 12 * 7) * ((n + 127) // 128) if args.model == "bert" else (1 + 12 * 7 + 3) * ((n + 63) // 64))
-            workload = (f"{'monoBERT' if args.model == 'bert' else 'CEDR-KNRM (13 similarity layers, cls=avg) on'} (BERT-base, random init) forward, {n} synthetic pairs per GPU per step, L={BERT_L} (|q|={Q}, doc truncated to "
-                        f"{BERT_L - Q - 3}), bf16x3 parity mode; bounded sample of BASELINE.json configs[3] (1000 q x 1000 docs)")
+            launches = args.steps * ((2 + 12 * 7) * ((n + 127) // 128) if args.model == "bert" else (1 + 12 * 7 + 4) * ((n + 127) // 128) if args.model == "cedrknrm"
+                                    else (1 + 12 * 7 + 3 + 2 * 7) * ((n * PARADE_P + 127) // 128))
+            names = {"bert": "monoBERT", "cedrknrm": "CEDR-KNRM (13 similarity layers, cls=avg) on", "parade": f"PARADE (transformer aggregation, {PARADE_P} passages of L={PARADE_L}) on"}
+            shape = (f"L={BERT_L} (|q|={Q}, doc truncated to {BERT_L - Q - 3})" if args.model != "parade"
+                     else f"|q|={Q}, |d|=512 as {PARADE_P} passages of {PARADE_L - Q - 3} tokens")
+            workload = (f"{names[args.model]} (BERT-base, random init) forward, {n} synthetic pairs per GPU per step, {shape}, bf16x3 parity mode; "
+                        f"bounded sample of BASELINE.json configs[3] (1000 q x 1000 docs)")
             l2 = "activations of one 128-sequence chunk (~2 GB) exceed L2; weights (0.35 GB as bf16 hi/lo planes) stream from HBM/L2"
         else:
             achieved = ALGO_BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
