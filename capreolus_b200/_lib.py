@@ -64,6 +64,8 @@ SIGNATURES = {
                                       _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_assemble_pairs": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, _f32p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     _i64p, _i64p, _f32p, c_void_p]),
+    "capr_assemble_bert_pairs": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, _i64p, _i64p, _i64p, c_void_p]),
     "capr_rank_by_query": (c_int, [_f32p, c_void_p, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
     "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),

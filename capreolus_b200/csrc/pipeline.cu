@@ -57,6 +57,59 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(const AssembleArgs 
   }
 }
 
+// ---- BERT passage rows ---------------------------------------------------------------------------------------------------
+// BertPassage._get_sliding_window_passages + _prepare_bert_input (capreolus/extractor/bertpassage.py:203-232, 268-284) on
+// WordPiece ids: passage p = doc[p*stride : p*stride + passagelen] (the first `P` windows; exhausted documents give the one-token
+// pad passage), row = [CLS] query [SEP] passage [SEP] [PAD]...; mask = (token != pad) on the written part, 0 on the padding;
+// segment = 0 for [CLS] query [SEP], 1 from there to the end INCLUDING the padding.  One warp per (pair, passage) row.
+struct BertAssembleArgs {
+  const int* q_store;
+  const long long* q_off;
+  const int* d_store;
+  const long long* d_off;
+  const int* qidx;
+  const int* didx;
+  int N, P, L, maxqlen, padq, passagelen, stride, n_queries, n_docs, cls_id, sep_id, pad_id;
+  long long* ids;
+  long long* mask;
+  long long* seg;
+};
+
+__global__ void __launch_bounds__(256) assemble_bert_kernel(const BertAssembleArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < (long long)a.N * a.P; row += nwarps) {
+    const int n = (int)(row / a.P), p = (int)(row - (long long)n * a.P);
+    const int qi = a.qidx[n], di = a.didx[n];
+    long long qbeg = 0, qlen = 0, dbeg = 0, dlen = 0;
+    if (qi >= 0 && qi < a.n_queries) qbeg = a.q_off[qi], qlen = a.q_off[qi + 1] - qbeg;
+    if (di >= 0 && di < a.n_docs) dbeg = a.d_off[di], dlen = a.d_off[di + 1] - dbeg;
+    if (qlen > a.maxqlen) qlen = a.maxqlen;                   // "Truncating query" (l.270-272)
+    const int qeff = a.padq ? a.maxqlen : (int)qlen;          // padq pads the query to maxqlen with [PAD] (l.274-275)
+    const long long start = (long long)p * a.stride;
+    const bool real = start < dlen;                           // else: the pad passage [pad_tok] (l.230)
+    long long plen = real ? dlen - start : 1;
+    if (plen > a.passagelen && real) plen = a.passagelen;
+    const int room = a.L - qeff - 3;                          // psg_toks[: maxseqlen - len(query_toks) - 3] (l.276)
+    if (plen > room) plen = room > 0 ? room : 0;
+    const int sep1 = qeff + 1, pbeg = qeff + 2, sep2 = pbeg + (int)plen;
+    for (int t = lane; t < a.L; t += 32) {
+      long long tok = a.pad_id;
+      bool written = false;
+      if (t == 0) tok = a.cls_id, written = true;
+      else if (t < sep1) tok = (t - 1 < qlen) ? a.q_store[qbeg + t - 1] : a.pad_id, written = true;
+      else if (t == sep1) tok = a.sep_id, written = true;
+      else if (t < sep2) tok = real ? a.d_store[dbeg + start + (t - pbeg)] : a.pad_id, written = true;
+      else if (t == sep2) tok = a.sep_id, written = true;
+      const size_t o = (size_t)row * a.L + t;
+      a.ids[o] = tok;
+      a.mask[o] = (written && tok != a.pad_id) ? 1 : 0;
+      a.seg[o] = t < pbeg ? 0 : 1;
+    }
+  }
+}
+
 // ---- per-query ranking -------------------------------------------------------------------------------------------
 // key = (monotone image of the fp16-rounded score) << 32 | (0xffffffff - position): sorting keys DESCENDING gives
 // score descending, ties by ascending position = Python's stable sorted(..., reverse=True) over insertion order.
@@ -120,6 +173,26 @@ int capr_assemble_pairs(const int32_t* q_store, const int64_t* q_off, int n_quer
   const long long want = ((long long)N + 7) / 8;
   const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
   assemble_pairs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+int capr_assemble_bert_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off,
+                             int n_docs, const int32_t* qidx, const int32_t* didx, int N, int P, int L, int maxqlen, int padq, int passagelen,
+                             int stride, int cls_id, int sep_id, int pad_id, int64_t* ids, int64_t* mask, int64_t* seg, capr_stream_t stream) {
+  const char* fn = "capr_assemble_bert_pairs";
+  CAPR_REQUIRE(N >= 0 && P > 0 && L > 3 && maxqlen >= 0 && passagelen > 0 && stride > 0 && n_queries >= 0 && n_docs >= 0, CAPR_ERR_BAD_SHAPE,
+               "%s: bad shape N=%d P=%d L=%d maxqlen=%d passagelen=%d stride=%d", fn, N, P, L, maxqlen, passagelen, stride);
+  CAPR_REQUIRE(maxqlen + 3 <= L, CAPR_ERR_BAD_SHAPE, "%s: maxqlen=%d does not fit in maxseqlen=%d", fn, maxqlen, L);
+  if (N == 0) return CAPR_OK;
+  CAPR_REQUIRE(q_store && q_off && d_store && d_off && qidx && didx && ids && mask && seg, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  BertAssembleArgs a{q_store, (const long long*)q_off, d_store, (const long long*)d_off, qidx, didx, N, P, L, maxqlen, padq, passagelen, stride,
+                     n_queries, n_docs, cls_id, sep_id, pad_id, (long long*)ids, (long long*)mask, (long long*)seg};
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  const long long want = ((long long)N * P + 7) / 8;
+  const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+  assemble_bert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }

@@ -143,6 +143,36 @@ class PairAssembler:
         return out
 
 
+class BertPairAssembler:
+    """``capr_assemble_bert_pairs``: (query index, doc index) vectors -> ``pos_bert_input / pos_mask / pos_seg [N,P,L]`` int64, the
+    rows ``BertPassage.id2vec`` builds per pair (``capreolus/extractor/bertpassage.py:203-232, 268-346``; sliding-window
+    passages).  The stores hold WordPiece ids (the tokenizer stays on the host, once per collection)."""
+
+    def __init__(self, queries: PackedIdStore, docs: PackedIdStore, maxqlen: int, maxseqlen: int, numpassages: int, passagelen: int, stride: int,
+                 device, padq: bool = False, cls_id: int = 101, sep_id: int = 102, pad_id: int = 0):
+        self.device = torch.device(device)
+        self.queries, self.docs = queries.to(self.device), docs.to(self.device)
+        self.Q, self.L, self.P = int(maxqlen), int(maxseqlen), int(numpassages)
+        self.passagelen, self.stride, self.padq = int(passagelen), int(stride), bool(padq)
+        self.cls_id, self.sep_id, self.pad_id = int(cls_id), int(sep_id), int(pad_id)
+
+    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None) -> dict:
+        from capreolus_b200 import _lib
+
+        _lib.require_cuda(qidx, didx)
+        if qidx.dtype != torch.int32 or didx.dtype != torch.int32:
+            raise ValueError("BertPairAssembler.assemble: index vectors must be int32")
+        n = qidx.shape[0]
+        if out is None:
+            out = {k: torch.empty((n, self.P, self.L), dtype=torch.int64, device=self.device) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+        q, d = self.queries, self.docs
+        _lib.check(_lib.lib().capr_assemble_bert_pairs(
+            q.flat.data_ptr(), q.offsets.data_ptr(), len(q), d.flat.data_ptr(), d.offsets.data_ptr(), len(d), qidx.contiguous().data_ptr(),
+            didx.contiguous().data_ptr(), n, self.P, self.L, self.Q, int(self.padq), self.passagelen, self.stride, self.cls_id, self.sep_id,
+            self.pad_id, out["pos_bert_input"].data_ptr(), out["pos_mask"].data_ptr(), out["pos_seg"].data_ptr(), _lib.current_stream(self.device)))
+        return out
+
+
 def rank_by_query(scores: torch.Tensor, seg_off: torch.Tensor, max_segment: int):
     """``capr_rank_by_query``: (float16-rounded scores ``[N]`` fp32, per-query order ``[N]`` int32); see include/capr_b200.h."""
     from capreolus_b200 import _lib
@@ -192,7 +222,7 @@ class RunPredictor:
         bufs = None
         for lo in range(0, n, self.chunk):
             hi = min(n, lo + self.chunk)
-            if bufs is None or bufs["query"].shape[0] != hi - lo:
+            if bufs is not None and next(iter(bufs.values())).shape[0] != hi - lo:
                 bufs = None
             bufs = self.assembler.assemble(qd[lo:hi], dd[lo:hi], bufs)
             scores[lo:hi] = reranker.test(bufs).view(-1)

@@ -181,6 +181,15 @@ int capr_convknrm_forward(const int64_t* query, const int64_t* doc, int B, int Q
 int capr_assemble_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off,
                         int n_docs, const float* idf_store, const int32_t* qidx, const int32_t* didx, int N, int Q, int D,
                         int64_t* query_out, int64_t* doc_out, float* idf_out, capr_stream_t stream);
+/* capr_assemble_bert_pairs: the same for the BERT rerankers -- BertPassage._get_sliding_window_passages + _prepare_bert_input
+ * (capreolus/extractor/bertpassage.py:203-232, 268-284) on WordPiece ids: per pair P passage rows
+ * [CLS] query [SEP] doc[p*stride : p*stride+passagelen] [SEP] [PAD]..., query truncated to maxqlen (padded to it when padq),
+ * passage truncated to L - len(query) - 3, exhausted documents give the one-token pad passage; mask = 1 on written tokens
+ * != pad_id; segment = 0 for [CLS] query [SEP] and 1 to the end including the padding.  ids / mask / seg: [N, P, L] int64. */
+int capr_assemble_bert_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off,
+                             int n_docs, const int32_t* qidx, const int32_t* didx, int N, int P, int L, int maxqlen, int padq,
+                             int passagelen, int stride, int cls_id, int sep_id, int pad_id, int64_t* ids, int64_t* mask, int64_t* seg,
+                             capr_stream_t stream);
 /* capr_rank_by_query replaces the float16 rounding of PytorchTrainer.predict (capreolus/trainer/pytorch.py:345-348) and the
  * per-query sort of Searcher.write_trec_run (capreolus/searcher/__init__.py:48-58).  Pairs of one query are contiguous:
  * seg_off [n_queries+1] int64.  rounded [N] (nullable) = float(float16(score)); order [N]: for query q, order[seg_off[q]+r]

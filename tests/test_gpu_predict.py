@@ -135,3 +135,71 @@ def test_run_predictor_matches_reference_predict_loop(tmp_path):
     assert (tmp_path / "out" / "run.txt").read_text() == (tmp_path / "ref.txt").read_text()
     with pytest.raises(KeyError, match="none features"):
         RunPredictor(asm).predict(rr, {"100": ["nosuchdoc"]})
+
+
+def _bert_rows(query, doc, P, L, maxqlen, passagelen, stride, padq, CLS=101, SEP=102, PAD=0):
+    """bertpassage.py:203-232 (sliding windows) + 268-284 (_prepare_bert_input) on token-id lists."""
+    passages = [doc[i:i + passagelen] for i in range(0, len(doc), stride)]
+    passages = passages[:P] if len(passages) > P else passages + [[PAD] for _ in range(P - len(passages))]
+    q = query[:maxqlen] if len(query) > maxqlen else (_padlist(query, maxqlen, PAD) if padq else list(query))
+    rows = []
+    for psg in passages:
+        psg = psg[: L - len(q) - 3]
+        line = [CLS] + q + [SEP] + list(psg) + [SEP]
+        padded = _padlist(line, L, PAD)
+        mask = [1 if t != PAD else 0 for t in line] + [0] * (len(padded) - len(line))
+        seg = [0] * (len(q) + 2) + [1] * (len(padded) - len(q) - 2)
+        rows.append((padded, mask[:L], seg[:L]))
+    return rows
+
+
+@pytest.mark.parametrize("padq", [False, True])
+def test_assemble_bert_pairs_equals_the_reference_extractor_logic(padq):
+    from capreolus_b200.predict import BertPairAssembler, PackedIdStore
+
+    P, L, maxqlen, passagelen, stride, V = 4, 48, 8, 20, 15, 30522
+    rng = np.random.default_rng(12)
+    queries = {str(i): rng.integers(1000, V, size=rng.integers(1, 14)).tolist() for i in range(6)}
+    docs = {f"d{i}": rng.integers(1000, V, size=n).tolist() for i, n in enumerate([0, 1, 14, 15, 16, 40, 61, 200, 33, 75])}
+    asm = BertPairAssembler(PackedIdStore.from_lists(queries), PackedIdStore.from_lists(docs), maxqlen, L, P, passagelen, stride, DEV, padq=padq)
+    qi = rng.integers(0, len(queries), size=64).astype(np.int32)
+    di = rng.integers(0, len(docs), size=64).astype(np.int32)
+    out = asm.assemble(torch.from_numpy(qi).to(DEV), torch.from_numpy(di).to(DEV))
+    qn, dn = list(queries), list(docs)
+    for n in range(64):
+        want = _bert_rows(queries[qn[qi[n]]], docs[dn[di[n]]], P, L, maxqlen, passagelen, stride, padq)
+        for p, (ids, mask, seg) in enumerate(want):
+            assert out["pos_bert_input"][n, p].tolist() == ids, (n, p)
+            assert out["pos_mask"][n, p].tolist() == mask, (n, p)
+            assert out["pos_seg"][n, p].tolist() == seg, (n, p)
+
+
+def test_run_predictor_drives_a_bert_reranker_from_a_packed_store():
+    """RunPredictor + BertPairAssembler + PTBERTMaxP == scoring the rows built by the reference extractor logic."""
+    from capreolus_b200 import reranker as R
+    from capreolus_b200.predict import BertPairAssembler, PackedIdStore, RunPredictor
+
+    P, L, maxqlen, passagelen, stride = 2, 48, 6, 24, 20
+    cfg = dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, vocab_size=1000, max_position_embeddings=64)
+    rng = np.random.default_rng(3)
+    queries = {str(i): rng.integers(200, 1000, size=rng.integers(1, 9)).tolist() for i in range(4)}
+    docs = {f"d{i}": rng.integers(200, 1000, size=rng.integers(1, 70)).tolist() for i in range(30)}
+
+    class Ext:
+        embeddings = None
+        config = {"numpassages": P, "maxseqlen": L}
+
+    torch.manual_seed(0)
+    rr = R.PTBERTMaxP(dict(pretrained=cfg), provide={"extractor": Ext()})
+    rr.build_model().to(DEV).eval()
+    dn = list(docs)
+    cands = {q: [dn[j] for j in rng.choice(len(dn), size=7, replace=False)] for q in queries}
+    asm = BertPairAssembler(PackedIdStore.from_lists(queries), PackedIdStore.from_lists(docs), maxqlen, L, P, passagelen, stride, DEV)
+    preds = RunPredictor(asm, chunk=10).predict(rr, cands)
+    rows = [(q, d) for q in cands for d in cands[q]]
+    built = [_bert_rows(queries[q], docs[d], P, L, maxqlen, passagelen, stride, False) for q, d in rows]
+    batch = {k: torch.tensor([[r[i] for r in b] for b in built], device=DEV) for i, k in enumerate(("pos_bert_input", "pos_mask", "pos_seg"))}
+    with torch.no_grad():
+        scores = rr.test(batch).view(-1).cpu().numpy()
+    for (q, d), s in zip(rows, scores):
+        assert preds[q][d] == s.astype(np.float16).item()
