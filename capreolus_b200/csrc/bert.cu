@@ -339,7 +339,6 @@ struct Model {
   int sms = 0;
   bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
   bool attention_v1 = false;    // CAPR_BERT_ATTENTION=v1: the first tensor-core attention (128 queries per CTA), for A/B tests
-  bool attention_v3 = false;    // CAPR_BERT_ATTENTION=v3: two softmax threads per row (16 softmax warps); measured equal to v2, kept for A/B tests
   bool gemm_pairs = true;       // CAPR_BERT_GEMM=1cta: force the one-CTA GEMM (A/B tests)
   int max_pairs = 0;            // co-resident CTA pairs of gemm2_kernel (cudaOccupancyMaxActiveClusters)
 };
@@ -502,7 +501,6 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
     const char* e = getenv("CAPR_BERT_ATTENTION");
     m->ffma_attention = e && e[0] == 'f';
     m->attention_v1 = e && e[0] == 'v' && e[1] == '1';
-    m->attention_v3 = e && e[0] == 'v' && e[1] == '3';
     const char* ge = getenv("CAPR_BERT_GEMM");
     m->gemm_pairs = !(ge && ge[0] == '1');
   }
@@ -644,10 +642,12 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     }
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
-    CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A3_SMEM));
   }
   const char* adbg = getenv("CAPR_ATTN_DEBUG");
-  const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo, adbg ? atoi(adbg) : 0};
+  // CAPR_ATTN_TRACE=<device pointer, decimal>: 256 int64 clock stamps of one CTA of attention_tc2_kernel (scripts/attn_trace.py)
+  const char* atr = getenv("CAPR_ATTN_TRACE");
+  const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo, adbg ? atoi(adbg) : 0,
+                      atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr};
   const int att_tc2_grid = n_seq * heads * ((L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ));
   const AttnArgs at{L, H, heads, n_seq, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
   const int att_tc_grid = n_seq * heads * ((L + AT_BQ - 1) / AT_BQ);
@@ -656,7 +656,6 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     if (tc_attention) {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_SPLIT, nullptr, nullptr, qkv_hi, qkv_lo, st))) return rc;
       if (m->attention_v1) attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
-      else if (m->attention_v3) attention_tc3_kernel<<<att_tc2_grid, A3_THREADS, A3_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
       else attention_tc2_kernel<<<att_tc2_grid, A2_THREADS, A2_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
       CAPR_CHECK_CUDA(cudaGetLastError());
     } else {

@@ -15,6 +15,10 @@
 //   * P is packed with cvt.rn.bf16x2.f32 (two values per instruction).
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = softmax of query block 0, 8-11 = softmax of block 1.
 // TMEM: S[block][2 buffers][64 cols] at 0..255, O[block][64 cols] at 256..383.
+// K/V tiles go through a THREE-stage ring: the clock64 trace of a CTA (scripts/attn_trace.py) showed the two-stage ring exposing
+// the whole TMA round trip (~2 200 cycles) every tile -- the stage of tile t is only released when P.V(t) of the second block
+// completes, and the MMA warp then sat on kv_full(t+2) with P(t+1) already published.  The key mask is kept as 16 ballot words
+// (64 B instead of a 2 KB float bias array) to make room for the third stage.
 #pragma once
 #include "bert_attn.cuh"
 
@@ -23,9 +27,10 @@ namespace bert {
 
 constexpr int A2_BLOCKS = 2;                    // query blocks of AT_BQ rows per CTA
 constexpr int A2_THREADS = 384;
-constexpr int A2_KV_STAGES = 2;
+constexpr int A2_KV_STAGES = 3;               // the K/V TMA round trip (~2 200 cycles, traced) needs two tiles of prefetch to hide
 constexpr float A2_RESCALE_THRESHOLD = 8.0f;    // log2 units
-constexpr size_t A2_SMEM = 1024 + A2_BLOCKS * 2 * AT_Q_BYTES + A2_KV_STAGES * AT_KV_STAGE_BYTES + A2_BLOCKS * 2 * AT_P_BYTES + AT_MAX_L * 4 + 512;
+constexpr size_t A2_SMEM = 1024 + A2_BLOCKS * 2 * AT_Q_BYTES + A2_KV_STAGES * AT_KV_STAGE_BYTES + A2_BLOCKS * 2 * AT_P_BYTES + AT_MAX_L / 8 + 512;
+static_assert(A2_SMEM <= 232448, "attention_tc2_kernel: shared memory budget");
 
 struct Attn2Args {
   int L, H, heads, n_seq;
@@ -35,7 +40,11 @@ struct Attn2Args {
   __nv_bfloat16* ctx_hi;  // [T, H]
   __nv_bfloat16* ctx_lo;
   int debug;              // profiling only (CAPR_ATTN_DEBUG; results invalid): 1 no softmax math, 2 no P.V MMAs, 4 no K/V reloads, 8 no Q.K MMAs
+  long long* trace;       // profiling only (CAPR_ATTN_TRACE): CTA 0 of the grid records clock64 stamps, [role][event] (see TR_* below)
 };
+
+// trace layout: 64 slots per role; roles: 0 producer, 1 MMA, 2 softmax block 0 (warp 4), 3 softmax block 1 (warp 8)
+#define CAPR_TR(role, slot) do { if (a.trace && blockIdx.x == 148 && lane == 0 && (slot) < 64) a.trace[(role) * 64 + (slot)] = clock64(); } while (0)
 
 // (hi, lo) bf16 split of two values at once; returns the packed words {lo16 = a, hi16 = b}
 __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hw, uint32_t& lw) {
@@ -54,17 +63,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   unsigned char* sQ = smem;                                          // [block][hi | lo]
   unsigned char* sKV = sQ + A2_BLOCKS * 2 * AT_Q_BYTES;              // [stage][K_hi, K_lo, V_hi, V_lo]
   unsigned char* sP = sKV + A2_KV_STAGES * AT_KV_STAGE_BYTES;        // [block][hi | lo]
-  float* kbias = reinterpret_cast<float*>(sP + A2_BLOCKS * 2 * AT_P_BYTES);  // [AT_MAX_L]  0 or -inf per key
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbias + AT_MAX_L);
+  uint32_t* kmask = reinterpret_cast<uint32_t*>(sP + A2_BLOCKS * 2 * AT_P_BYTES);  // [AT_MAX_L / 32] bit j = key j is attended to
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kmask + AT_MAX_L / 32);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [block][2]
-  uint64_t* s_empty = bars + 9;       // [block][2]
-  uint64_t* p_full = bars + 13;       // [block]
-  uint64_t* p_empty = bars + 15;      // [block]
-  uint64_t* o_full = bars + 17;       // [block]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* kv_full = bars + 1;       // [3]
+  uint64_t* kv_empty = bars + 4;      // [3]
+  uint64_t* s_full = bars + 7;        // [block][2]
+  uint64_t* s_empty = bars + 11;      // [block][2]
+  uint64_t* p_full = bars + 15;       // [block]
+  uint64_t* p_empty = bars + 17;      // [block]
+  uint64_t* o_full = bars + 19;       // [block]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   int* s_kv_len = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -93,19 +102,22 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  int last = 0;
-  for (int j = tid; j < AT_MAX_L; j += A2_THREADS) {
-    const bool on = j < a.L && mrow[j] != 0;
-    kbias[j] = on ? 0.f : -INFINITY;
-    if (on) last = j + 1;
+  // key mask as a bitmask (one ballot per 32 keys) and the position after the last attended key
+  for (int w = warp; w < AT_MAX_L / 32; w += A2_THREADS / 32) {
+    const int j = w * 32 + lane;
+    const unsigned bits = __ballot_sync(0xffffffffu, j < a.L && mrow[j] != 0);
+    if (lane == 0) {
+      kmask[w] = bits;
+      if (bits) atomicMax(s_kv_len, w * 32 + 32 - __clz(bits));
+    }
   }
-  if (last) atomicMax(s_kv_len, last);
   __syncthreads();
   const int n_tiles = (*s_kv_len + AT_BK - 1) / AT_BK;
   const int col_q = head * AT_DH, col_k = a.H + head * AT_DH, col_v = 2 * a.H + head * AT_DH;
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    CAPR_TR(0, 0);  // prologue done
     if (n_tiles > 0) {
       if (tc::elect_one()) {
         tc::mbar_expect_tx(q_full, A2_BLOCKS * 2 * AT_Q_BYTES);
@@ -121,6 +133,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         tc::mbar_wait(&kv_empty[stage], phase ^ 1);
+        CAPR_TR(0, 1 + t);  // producer: stage free, issuing loads of tile t
         unsigned char* st = sKV + stage * AT_KV_STAGE_BYTES;
         const int row = tok0 + t * AT_BK;
         if ((a.debug & 4) && t >= A2_KV_STAGES) {
@@ -142,10 +155,12 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       const uint32_t idesc_qk = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_BK);
       const uint32_t idesc_pv = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_DH) | (1u << 16);  // B is MN-major (V: dims contiguous)
       tc::mbar_wait(q_full, 0);
+      CAPR_TR(1, 0);  // MMA: Q landed
       auto issue_qk = [&](int g, int t) {
         const int stage = t % A2_KV_STAGES, buf = t & 1;
         tc::mbar_wait(&kv_full[stage], (uint32_t)((t / A2_KV_STAGES) & 1));
         tc::mbar_wait(&s_empty[g * 2 + buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+        CAPR_TR(1, 1 + 4 * t + g);  // MMA: issuing QK(g, t)
         tc::tc_fence_after();
         const uint32_t q_hi = tc::smem_u32(sQ + (g * 2) * AT_Q_BYTES), q_lo = q_hi + AT_Q_BYTES;
         const uint32_t k_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES), k_lo = k_hi + AT_T_BYTES;
@@ -165,6 +180,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       auto issue_pv = [&](int g, int t) {
         const int stage = t % A2_KV_STAGES;
         tc::mbar_wait(&p_full[g], (uint32_t)(t & 1));
+        CAPR_TR(1, 1 + 4 * t + 2 + g);  // MMA: issuing PV(g, t)
         tc::tc_fence_after();
         const uint32_t v_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES + 2 * AT_T_BYTES), v_lo = v_hi + AT_T_BYTES;
         const uint32_t p_hi = tc::smem_u32(sP + (g * 2) * AT_P_BYTES), p_lo = p_hi + AT_P_BYTES;
@@ -206,6 +222,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       tc::mbar_wait(&s_full[g * 2 + buf], (uint32_t)((t >> 1) & 1));
+      if (quarter == 0) CAPR_TR(2 + g, 4 * t);  // softmax: S(t) visible
       tc::tc_fence_after();
       float s[AT_BK];
       {
@@ -225,16 +242,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
         continue;
       }
       float mx = -INFINITY;
-      const float4* kb4 = reinterpret_cast<const float4*>(kbias + t * AT_BK);
+      const uint32_t km0 = kmask[2 * t], km1 = kmask[2 * t + 1];
+      if ((km0 & km1) == 0xffffffffu) {  // CTA-uniform fast path: every key of the tile is attended to
 #pragma unroll
-      for (int i = 0; i < AT_BK / 4; ++i) {
-        const float4 b = kb4[i];
-        s[4 * i] = fmaf(s[4 * i], a.scale_log2e, b.x);
-        s[4 * i + 1] = fmaf(s[4 * i + 1], a.scale_log2e, b.y);
-        s[4 * i + 2] = fmaf(s[4 * i + 2], a.scale_log2e, b.z);
-        s[4 * i + 3] = fmaf(s[4 * i + 3], a.scale_log2e, b.w);
-        mx = fmaxf(mx, fmaxf(fmaxf(s[4 * i], s[4 * i + 1]), fmaxf(s[4 * i + 2], s[4 * i + 3])));
+        for (int i = 0; i < AT_BK; ++i) s[i] *= a.scale_log2e;
+      } else {
+#pragma unroll
+        for (int i = 0; i < AT_BK; ++i) s[i] = (((i < 32 ? km0 : km1) >> (i & 31)) & 1u) ? s[i] * a.scale_log2e : -INFINITY;
       }
+#pragma unroll
+      for (int i = 0; i < AT_BK / 4; ++i) mx = fmaxf(mx, fmaxf(fmaxf(s[4 * i], s[4 * i + 1]), fmaxf(s[4 * i + 2], s[4 * i + 3])));
       if (t == 0) {
         m_ref = mx;
       } else {
@@ -261,7 +278,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       }
       const bool dead = m_ref == -INFINITY;
       float rs = 0.f;
+      if (quarter == 0) CAPR_TR(2 + g, 4 * t + 1);  // softmax: max known, waiting for the P buffer
       tc::mbar_wait(&p_empty[g], (uint32_t)((t & 1) ^ 1));  // P.V of tile t-1 is done reading the P buffer
+      if (quarter == 0) CAPR_TR(2 + g, 4 * t + 2);  // softmax: P buffer free
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 keys per 16-byte chunk
         uint32_t hw[4], lw[4];
@@ -278,12 +297,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       }
       tc::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       tc::mbar_arrive(&p_full[g]);
+      if (quarter == 0) CAPR_TR(2 + g, 4 * t + 3);  // softmax: P(t) published
       l_run += rs;
     }
     if (n_tiles > 0) {
       tc::mbar_wait(&o_full[g], (uint32_t)((n_tiles - 1) & 1));
       tc::tc_fence_after();
     }
+    if (quarter == 0) CAPR_TR(2 + g, 60);  // softmax: last P.V landed
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     const size_t off = (size_t)(tok0 + qrow) * a.H + head * AT_DH;
 #pragma unroll
@@ -318,286 +339,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   }
 }
 
-
-// ---- third generation: 16 softmax warps (two threads per query row) -------------------------------------------------------
-// attention_tc2_kernel issues at 25 % of the slots (ncu: 24.8 % issue active, tensor pipe 24.8 %): the one-row-per-thread softmax
-// is a long dependent instruction stream and two warps per scheduler do not hide its latencies.  Here every row is shared by
-// two threads in two different warps (keys 0-31 / 32-63 of each tile): half the instructions per thread, four softmax warps per
-// scheduler.  Everything else (TMA / MMA protocol, O in TMEM, lazy rescale) is the v2 design.
-constexpr int A3_THREADS = 640;
-constexpr size_t A3_SMEM = A2_SMEM + 2 * A2_BLOCKS * 2 * AT_BQ * 4;
-
-__global__ void __launch_bounds__(A3_THREADS, 1)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
-                     const __grid_constant__ CUtensorMap tm_kv_hi, const __grid_constant__ CUtensorMap tm_kv_lo, const Attn2Args a) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;                                          // [block][hi | lo]
-  unsigned char* sKV = sQ + A2_BLOCKS * 2 * AT_Q_BYTES;              // [stage][K_hi, K_lo, V_hi, V_lo]
-  unsigned char* sP = sKV + A2_KV_STAGES * AT_KV_STAGE_BYTES;        // [block][hi | lo]
-  float* kbias = reinterpret_cast<float*>(sP + A2_BLOCKS * 2 * AT_P_BYTES);  // [AT_MAX_L]  0 or -inf per key
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kbias + AT_MAX_L);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [block][2]
-  uint64_t* s_empty = bars + 9;       // [block][2]
-  uint64_t* p_full = bars + 13;       // [block]
-  uint64_t* p_empty = bars + 15;      // [block]
-  uint64_t* o_full = bars + 17;       // [block]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-  int* s_kv_len = reinterpret_cast<int*>(tmem_slot + 1);
-  float* xch = reinterpret_cast<float*>(tmem_slot + 4);  // [parity][block][key half][128 rows] row-max / row-sum exchange
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int qblocks = (a.L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ);
-  const int qb = blockIdx.x % qblocks, head = (blockIdx.x / qblocks) % a.heads, seq = blockIdx.x / (qblocks * a.heads);
-  const int tok0 = seq * a.L;
-  const long long* mrow = a.mask + (size_t)seq * a.L;
-
-  if (tid == 0) {
-    tc::mbar_init(q_full, 1);
-    for (int i = 0; i < A2_KV_STAGES; ++i) tc::mbar_init(&kv_full[i], 1), tc::mbar_init(&kv_empty[i], 1);
-    for (int i = 0; i < 4; ++i) {
-      tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&s_empty[i], 8);  // one arrive per softmax warp of the block (4 row quarters x 2 key halves)
-    }
-    for (int g = 0; g < A2_BLOCKS; ++g) {
-      tc::mbar_init(&p_full[g], 256);  // every softmax thread publishes its half row of P
-      tc::mbar_init(&p_empty[g], 1);
-      tc::mbar_init(&o_full[g], 1);
-    }
-    tc::fence_barrier_init();
-    *s_kv_len = 0;
-  }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  int last = 0;
-  for (int j = tid; j < AT_MAX_L; j += A3_THREADS) {
-    const bool on = j < a.L && mrow[j] != 0;
-    kbias[j] = on ? 0.f : -INFINITY;
-    if (on) last = j + 1;
-  }
-  if (last) atomicMax(s_kv_len, last);
-  __syncthreads();
-  const int n_tiles = (*s_kv_len + AT_BK - 1) / AT_BK;
-  const int col_q = head * AT_DH, col_k = a.H + head * AT_DH, col_v = 2 * a.H + head * AT_DH;
-
-  if (warp == 0) {
-    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-    if (n_tiles > 0) {
-      if (tc::elect_one()) {
-        tc::mbar_expect_tx(q_full, A2_BLOCKS * 2 * AT_Q_BYTES);
-        for (int g = 0; g < A2_BLOCKS; ++g) {
-          long long row = (long long)tok0 + (qb * A2_BLOCKS + g) * AT_BQ;
-          if (row >= a.total_rows) row = (long long)tok0 + qb * A2_BLOCKS * AT_BQ;  // block entirely past the data: its rows are never stored
-          tc::tma_load_2d(sQ + (g * 2) * AT_Q_BYTES, &tm_q_hi, q_full, col_q, (int)row);
-          tc::tma_load_2d(sQ + (g * 2 + 1) * AT_Q_BYTES, &tm_q_lo, q_full, col_q, (int)row);
-        }
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        tc::mbar_wait(&kv_empty[stage], phase ^ 1);
-        unsigned char* st = sKV + stage * AT_KV_STAGE_BYTES;
-        const int row = tok0 + t * AT_BK;
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&kv_full[stage], AT_KV_STAGE_BYTES);
-          tc::tma_load_2d(st, &tm_kv_hi, &kv_full[stage], col_k, row);
-          tc::tma_load_2d(st + AT_T_BYTES, &tm_kv_lo, &kv_full[stage], col_k, row);
-          tc::tma_load_2d(st + 2 * AT_T_BYTES, &tm_kv_hi, &kv_full[stage], col_v, row);
-          tc::tma_load_2d(st + 3 * AT_T_BYTES, &tm_kv_lo, &kv_full[stage], col_v, row);
-        }
-        __syncwarp();
-        if (++stage == A2_KV_STAGES) stage = 0, phase ^= 1;
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    if (n_tiles > 0) {
-      const uint32_t idesc_qk = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_BK);
-      const uint32_t idesc_pv = tc::make_instr_desc(tc::FMT_BF16, AT_BQ, AT_DH) | (1u << 16);  // B is MN-major (V: dims contiguous)
-      tc::mbar_wait(q_full, 0);
-      auto issue_qk = [&](int g, int t) {
-        const int stage = t % A2_KV_STAGES, buf = t & 1;
-        tc::mbar_wait(&kv_full[stage], (uint32_t)((t / A2_KV_STAGES) & 1));
-        tc::mbar_wait(&s_empty[g * 2 + buf], (uint32_t)(((t >> 1) & 1) ^ 1));
-        tc::tc_fence_after();
-        const uint32_t q_hi = tc::smem_u32(sQ + (g * 2) * AT_Q_BYTES), q_lo = q_hi + AT_Q_BYTES;
-        const uint32_t k_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES), k_lo = k_hi + AT_T_BYTES;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(g * 128 + buf * AT_BK);
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < AT_DH / 16; ++k) {
-            const uint32_t ko = k * 32;
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, k != 0);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_lo + ko), idesc_qk, true);
-          }
-          tc::umma_commit(&s_full[g * 2 + buf]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int g, int t) {
-        const int stage = t % A2_KV_STAGES;
-        tc::mbar_wait(&p_full[g], (uint32_t)(t & 1));
-        tc::tc_fence_after();
-        const uint32_t v_hi = tc::smem_u32(sKV + stage * AT_KV_STAGE_BYTES + 2 * AT_T_BYTES), v_lo = v_hi + AT_T_BYTES;
-        const uint32_t p_hi = tc::smem_u32(sP + (g * 2) * AT_P_BYTES), p_lo = p_hi + AT_P_BYTES;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(256 + g * AT_DH);
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < AT_BK / 16; ++k) {
-            const uint32_t pk = k * 32;        // 16 keys = 32 bytes along P's K-major rows
-            const uint32_t vk = k * 16 * 128;  // 16 keys = 16 rows of the V tile
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, (t | k) != 0);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_lo + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, true);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_lo + vk), idesc_pv, true);
-          }
-          tc::umma_commit(&o_full[g]);
-          tc::umma_commit(&p_empty[g]);
-          if (g == A2_BLOCKS - 1) tc::umma_commit(&kv_empty[stage]);
-        }
-        __syncwarp();
-      };
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) issue_qk(0, t + 1);
-        issue_pv(0, t);
-        if (t + 1 < n_tiles) issue_qk(1, t + 1);
-        issue_pv(1, t);
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== softmax / output: TWO threads per query row, each owns 32 of the 64 keys of a tile ==========
-    // warps 4-7 / 8-11: block 0, keys 0-31 / 32-63 of every tile; warps 12-15 / 16-19: block 1.  The two threads of a row
-    // agree on the row max through shared memory (one 64-thread named barrier per tile), make the same lazy-rescale
-    // decision, rescale / finally store their own 32 columns of O, and add their partial row sums at the end.
-    const int sw = warp - 4;
-    const int g = sw >> 3, hsel = (sw >> 2) & 1, quarter = sw & 3;
-    const int row_in_blk = quarter * 32 + lane;
-    const int qrow = (qb * A2_BLOCKS + g) * AT_BQ + row_in_blk;  // position inside the sequence
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t o_tmem = tmem_base + lane_off + (uint32_t)(256 + g * AT_DH + hsel * 32);
-    const int pair_bar = 4 + g * 4 + quarter;  // named barrier of the two warps that share these 32 rows
-    float m_ref = -INFINITY, l_run = 0.f;
-    unsigned char* prow_hi = sP + (g * 2) * AT_P_BYTES + row_in_blk * 128;
-    unsigned char* prow_lo = prow_hi + AT_P_BYTES;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int buf = t & 1;
-      tc::mbar_wait(&s_full[g * 2 + buf], (uint32_t)((t >> 1) & 1));
-      tc::tc_fence_after();
-      float s[32];
-      tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(g * 128 + buf * AT_BK + hsel * 32), s);
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_empty[g * 2 + buf]);
-      float mx = -INFINITY;
-      const float4* kb4 = reinterpret_cast<const float4*>(kbias + t * AT_BK + hsel * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = kb4[i];
-        s[4 * i] = fmaf(s[4 * i], a.scale_log2e, b.x);
-        s[4 * i + 1] = fmaf(s[4 * i + 1], a.scale_log2e, b.y);
-        s[4 * i + 2] = fmaf(s[4 * i + 2], a.scale_log2e, b.z);
-        s[4 * i + 3] = fmaf(s[4 * i + 3], a.scale_log2e, b.w);
-        mx = fmaxf(mx, fmaxf(fmaxf(s[4 * i], s[4 * i + 1]), fmaxf(s[4 * i + 2], s[4 * i + 3])));
-      }
-      {  // row max over both key halves
-        float* mine = xch + (((t & 1) * A2_BLOCKS + g) * 2 + hsel) * AT_BQ + row_in_blk;
-        float* other = xch + (((t & 1) * A2_BLOCKS + g) * 2 + (hsel ^ 1)) * AT_BQ + row_in_blk;
-        *mine = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mx = fmaxf(mx, *other);
-      }
-      if (t == 0) {
-        m_ref = mx;
-      } else {
-        const bool need = mx > m_ref + A2_RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {
-          tc::mbar_wait(&o_full[g], (uint32_t)((t - 1) & 1));  // P.V of tile t-1 has landed; tile t is not issued before our p_full
-          tc::tc_fence_after();
-          const float factor = need ? ex2_approx(m_ref - mx) : 1.0f;
-          float o[32];
-          tc::tmem_ld_32x32(o_tmem, o);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= factor;
-          tc::tmem_st_32x32(o_tmem, o);
-          tc::tmem_st_wait();
-          tc::tc_fence_before();
-          l_run *= factor;
-          m_ref = need ? mx : m_ref;
-        }
-      }
-      const bool dead = m_ref == -INFINITY;
-      float rs = 0.f;
-      tc::mbar_wait(&p_empty[g], (uint32_t)((t & 1) ^ 1));  // P.V of tile t-1 is done reading the P buffer
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {  // 8 keys per 16-byte chunk; this thread owns chunks 4*hsel .. 4*hsel+3
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float p0 = dead ? 0.f : ex2_approx(s[c * 8 + 2 * j] - m_ref);
-          const float p1 = dead ? 0.f : ex2_approx(s[c * 8 + 2 * j + 1] - m_ref);
-          rs += p0 + p1;
-          split2_bf16(p0, p1, hw[j], lw[j]);
-        }
-        const int pos = ((hsel * 4 + c) ^ (row_in_blk & 7)) << 4;  // SWIZZLE_128B: chunk index XOR (row % 8)
-        *reinterpret_cast<uint4*>(prow_hi + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(prow_lo + pos) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-      tc::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      tc::mbar_arrive(&p_full[g]);
-      l_run += rs;
-    }
-    {  // row sum over both key halves (parity slot n_tiles & 1 was last used two tiles ago)
-      float* mine = xch + (((n_tiles & 1) * A2_BLOCKS + g) * 2 + hsel) * AT_BQ + row_in_blk;
-      float* other = xch + (((n_tiles & 1) * A2_BLOCKS + g) * 2 + (hsel ^ 1)) * AT_BQ + row_in_blk;
-      *mine = l_run;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      l_run += *other;
-    }
-    if (n_tiles > 0) {
-      tc::mbar_wait(&o_full[g], (uint32_t)((n_tiles - 1) & 1));
-      tc::tc_fence_after();
-    }
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    const size_t off = (size_t)(tok0 + qrow) * a.H + head * AT_DH + hsel * 32;
-    float o[32];
-    if (n_tiles > 0) {
-      tc::tmem_ld_32x32(o_tmem, o);
-      tc::tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    }
-    if (qrow < a.L) {
-      uint4* ph4 = reinterpret_cast<uint4*>(a.ctx_hi + off);
-      uint4* pl4 = reinterpret_cast<uint4*>(a.ctx_lo + off);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split2_bf16(o[c * 8 + 2 * j] * inv, o[c * 8 + 2 * j + 1] * inv, hw[j], lw[j]);
-        ph4[c] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        pl4[c] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
 
 }  // namespace bert
 }  // namespace capr
