@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
   static_assert((QT * CNT_PITCH_TC + MAX_SLOTS_TC + QT) <= SPARE_FLOATS, "DRMM scratch must fit behind the two half tiles");
   int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][CNT_PITCH_TC]
   float* ub = reinterpret_cast<float*>(cnt + QT * CNT_PITCH_TC);  // [MAX_SLOTS_TC]
@@ -303,7 +303,10 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
              nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
              simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}};
-  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, 0);
+  const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
+  const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
+  a.pr.deep = (atoms >= 3 && !(ring_env && ring_env[0] == '2')) ? 1 : 0;
+  const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);

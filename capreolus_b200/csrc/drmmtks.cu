@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmmtks_tc_kernel(cons
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
   float* z = spare_scratch(s);  // [QT] ffw output per query term
   const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
   if (is_producer_warp(warp)) {
@@ -163,7 +163,10 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
   CAPR_REQUIRE((((uintptr_t)table_hi | (uintptr_t)table_lo) & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table planes must be 16-byte aligned", fn);
   TksArgs a{simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0},
             topk, idf, ffw_w, ffw_b, gate_w, out_w, out_b, scores, topk_out};
-  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, 0);
+  const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
+  const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
+  a.pr.deep = (atoms >= 3 && !(ring_env && ring_env[0] == '2')) ? 1 : 0;
+  const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;

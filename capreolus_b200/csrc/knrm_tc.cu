@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K);
+  Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
   float* sPart = s.extra;  // [2][POOL_WARPS][KT] per-warp partial features, double-buffered by pair parity
   const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
 
@@ -211,7 +211,12 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, flags & 0xF00};
   a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2, a.scores = scores, a.feats = feats;
   const int KT = K <= 11 ? 11 : 16;
-  const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, (size_t)(2 * simtc::POOL_WARPS * KT) * sizeof(float));
+  const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
+  // deep ring (one query buffer, three doc stages) whenever the second query buffer is worth less than a doc stage;
+  // CAPR_SIM_RING=2 forces the default layout (A/B tests)
+  const char* ring_env = getenv("CAPR_SIM_RING");
+  a.pr.deep = (atoms >= 3 && !(ring_env && ring_env[0] == '2')) ? 1 : 0;
+  const size_t smem = simtc::smem_bytes(atoms, (size_t)(2 * simtc::POOL_WARPS * KT) * sizeof(float), a.pr.deep != 0);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;

@@ -42,7 +42,8 @@ constexpr int MAX_ATOMS = 5;                  // pitch <= 320
 constexpr int NT_DOCS = 256;                  // doc rows per MMA (N) = per work unit
 constexpr int Q_ATOM_BYTES = 64 * 128;        // [q_hi;q_lo] 64 rows x 128 B
 constexpr int D_STAGE_BYTES = NT_DOCS * 128;  // one plane (hi or lo) of 256 doc rows x one 64-element K atom = 32 KB
-constexpr int D_STAGES = 2;                   // ring depth
+constexpr int D_STAGES = 2;                   // ring depth of the default layout
+constexpr int MAX_D_STAGES = 3;               // "deep" layout: one query buffer, three doc stages (96 KB of gathers in flight)
 constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
 constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
 constexpr int POOL_WARPS = 8;                 // pipelined epilogue: pooling warps
@@ -69,21 +70,23 @@ struct Smem {
   float* extra;               // model-specific scratch
 };
 
-__host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes) {
-  return 1024 + (size_t)2 * atoms * Q_ATOM_BYTES + (size_t)D_STAGES * D_STAGE_BYTES + (size_t)SIM_ROWS * SIM_PITCH * 4 +
-         (size_t)(3 * QT + 3 * DT) * 4 + 16 * 8 + 16 + extra_bytes;
+// deep = false: two query buffers + two doc stages (default).  deep = true: ONE query buffer + THREE doc stages -- the gather
+// is latency bound (Little: bytes in flight / loaded L2 latency), so a third 32 KB stage buys more than the second query buffer.
+__host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes, bool deep = false) {
+  return 1024 + (size_t)(deep ? 1 : 2) * atoms * Q_ATOM_BYTES + (size_t)(deep ? MAX_D_STAGES : D_STAGES) * D_STAGE_BYTES +
+         (size_t)SIM_ROWS * SIM_PITCH * 4 + (size_t)(3 * QT + 3 * DT) * 4 + 18 * 8 + 16 + extra_bytes;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
+__device__ __forceinline__ Smem carve(unsigned char* raw, int atoms, bool deep = false) {
   Smem s;
   // (offset arithmetic instead of rounding the pointer as an integer: the compiler keeps the shared address space and
   // emits LDS/STS instead of generic loads)
   unsigned char* p = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   s.q0 = p;
   s.q_stride = atoms * Q_ATOM_BYTES;
-  p += 2 * atoms * Q_ATOM_BYTES;
+  p += (deep ? 1 : 2) * atoms * Q_ATOM_BYTES;
   s.d0 = p;
-  p += D_STAGES * D_STAGE_BYTES;
+  p += (deep ? MAX_D_STAGES : D_STAGES) * D_STAGE_BYTES;
   s.sim = reinterpret_cast<float*>(p);
   p += SIM_ROWS * SIM_PITCH * 4;
   s.qrow = reinterpret_cast<int*>(p);
@@ -92,10 +95,10 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms) {
   s.did = s.qid + 2 * QT;
   p += (3 * QT + 3 * DT) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
-  s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + D_STAGES, s.acc_full = b + 4 + 2 * D_STAGES,
-  s.acc_empty = b + 6 + 2 * D_STAGES;
-  s.half_full = b + 8 + 2 * D_STAGES, s.half_empty = b + 10 + 2 * D_STAGES;  // D_STAGES == 2: 16 barriers in all
-  p += 16 * 8;
+  s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + MAX_D_STAGES, s.acc_full = b + 4 + 2 * MAX_D_STAGES,
+  s.acc_empty = b + 6 + 2 * MAX_D_STAGES;
+  s.half_full = b + 8 + 2 * MAX_D_STAGES, s.half_empty = b + 10 + 2 * MAX_D_STAGES;  // 18 barriers in all
+  p += 18 * 8;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   s.extra = reinterpret_cast<float*>(p + 16);
   return s;
@@ -116,7 +119,11 @@ struct Problem {
   int debug;                // CAPR_DEBUG_* profiling switches (0 in production)
   int single;               // 1: use only query buffer 0 and TMEM accumulator buffer 0 (PACRR's conv-on-tensor-cores epilogue
                             // needs the second query buffer's shared memory and half of TMEM for itself)
+  int deep;                 // 1: the "deep" shared-memory layout (carve(..., true)): one query buffer, three doc stages
 };
+
+__device__ __forceinline__ int ring_depth(const Problem& pr) { return pr.deep ? MAX_D_STAGES : D_STAGES; }
+__device__ __forceinline__ bool one_qbuf(const Problem& pr) { return pr.single || pr.deep; }
 
 __device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
 
@@ -132,7 +139,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads =
       tc::mbar_init(&s.half_full[i], 2);  // the two q_hi draining warps
       tc::mbar_init(&s.half_empty[i], POOL_WARPS);
     }
-    for (int i = 0; i < D_STAGES; ++i) {
+    for (int i = 0; i < MAX_D_STAGES; ++i) {
       tc::mbar_init(&s.d_full[i], PROD_THREADS);
       tc::mbar_init(&s.d_empty[i], 1);
     }
@@ -175,8 +182,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
   uint32_t q_phase = 0, d_phase = 0;  // q_phase: one bit per buffer
   int d_stage = 0, it = 0;
+  const int nst = ring_depth(pr);
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
-    const int b = pr.single ? 0 : (it & 1);
+    const int b = one_qbuf(pr) ? 0 : (it & 1);
     prod_barrier();  // every producer thread is done reading the previous pair's rows
     if (ptid < QT) s.qrow[ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
     for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
@@ -215,7 +223,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
             }
           }
           cp_async_arrive_noinc(&s.d_full[d_stage]);
-          if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
+          if (++d_stage == nst) d_stage = 0, d_phase ^= 1;
         }
       }
     }
@@ -235,8 +243,9 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   const bool skip = (pr.debug & 0x400) != 0;
   uint32_t q_phase = 0, acc_phase = 0, d_phase = 0;  // q/acc: one bit per buffer
   int d_stage = 0, it = 0, unit = 0;
+  const int nst = ring_depth(pr);
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
-    const int b = pr.single ? 0 : (it & 1);
+    const int b = one_qbuf(pr) ? 0 : (it & 1);
     tc::mbar_wait(&s.q_full[b], (q_phase >> b) & 1);
     q_phase ^= 1u << b;
     const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.qbuf(b)));
@@ -262,7 +271,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
             tc::umma_commit(&s.d_empty[d_stage]);
           }
           __syncwarp();
-          if (++d_stage == D_STAGES) d_stage = 0, d_phase ^= 1;
+          if (++d_stage == nst) d_stage = 0, d_phase ^= 1;
         }
       }
       if (tc::elect_one()) {
