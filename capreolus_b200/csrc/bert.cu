@@ -19,6 +19,7 @@
 
 #include "bert_attn.cuh"
 #include "bert_attn2.cuh"
+#include "bert_attn3.cuh"
 #include "bert_gemm2.cuh"
 #include "tmap.cuh"
 
@@ -339,6 +340,7 @@ struct Model {
   int sms = 0;
   bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
   bool attention_v1 = false;    // CAPR_BERT_ATTENTION=v1: the first tensor-core attention (128 queries per CTA), for A/B tests
+  bool attention_v2 = false;    // CAPR_BERT_ATTENTION=v2: one CTA per (sequence, head, 256 queries) instead of the persistent kernel
   bool gemm_pairs = true;       // CAPR_BERT_GEMM=1cta: force the one-CTA GEMM (A/B tests)
   int max_pairs = 0;            // co-resident CTA pairs of gemm2_kernel (cudaOccupancyMaxActiveClusters)
 };
@@ -501,6 +503,7 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
     const char* e = getenv("CAPR_BERT_ATTENTION");
     m->ffma_attention = e && e[0] == 'f';
     m->attention_v1 = e && e[0] == 'v' && e[1] == '1';
+    m->attention_v2 = e && e[0] == 'v' && e[1] == '2';
     const char* ge = getenv("CAPR_BERT_GEMM");
     m->gemm_pairs = !(ge && ge[0] == '1');
   }
@@ -642,6 +645,7 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     }
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+    CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A4_SMEM));
   }
   const char* adbg = getenv("CAPR_ATTN_DEBUG");
   // CAPR_ATTN_TRACE=<device pointer, decimal>: 256 int64 clock stamps of one CTA of attention_tc2_kernel (scripts/attn_trace.py)
@@ -656,7 +660,8 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     if (tc_attention) {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_SPLIT, nullptr, nullptr, qkv_hi, qkv_lo, st))) return rc;
       if (m->attention_v1) attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
-      else attention_tc2_kernel<<<att_tc2_grid, A2_THREADS, A2_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
+      else if (m->attention_v2) attention_tc2_kernel<<<att_tc2_grid, A2_THREADS, A2_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
+      else attention_tc4_kernel<<<att_tc2_grid < m->sms ? att_tc2_grid : m->sms, A4_THREADS, A4_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
       CAPR_CHECK_CUDA(cudaGetLastError());
     } else {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;

@@ -77,6 +77,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   int* s_kv_len = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (warp == 0) CAPR_TR(0, 62);  // kernel entry
   const int qblocks = (a.L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ);
   const int qb = blockIdx.x % qblocks, head = (blockIdx.x / qblocks) % a.heads, seq = blockIdx.x / (qblocks * a.heads);
   const int tok0 = seq * a.L;
@@ -102,6 +103,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) CAPR_TR(0, 61);  // barriers + TMEM ready
   // key mask as a bitmask (one ballot per 32 keys) and the position after the last attended key
   for (int w = warp; w < AT_MAX_L / 32; w += A2_THREADS / 32) {
     const int j = w * 32 + lane;
@@ -333,6 +335,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (warp == 0) CAPR_TR(0, 63);  // all roles done
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);

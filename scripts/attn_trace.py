@@ -15,6 +15,7 @@ torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(4, 64)
 t0 = t[0, 0]
 rel = lambda x: int(x - t0) if x else None
+print("kernel entry", rel(t[0, 62]), "barriers+TMEM ready", rel(t[0, 61]), "all roles done", rel(t[0, 63]))
 print("producer: prologue done 0; loads of tile t issued at", [rel(x) for x in t[0, 1:9]])
 print("MMA: Q landed", rel(t[1, 0]))
 for tile in range(8):

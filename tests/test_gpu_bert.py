@@ -91,9 +91,9 @@ def test_bert_training_mode_is_rejected():
         rr.test(b)
 
 
-@pytest.mark.parametrize("variant", ["v1", "ffma"])
+@pytest.mark.parametrize("variant", ["v1", "v2", "ffma"])
 def test_bert_attention_variants_agree_with_the_default(variant, monkeypatch):
-    """The A/B attention kernels (CAPR_BERT_ATTENTION=v1 | ffma) stay parity-green against the same golden."""
+    """The A/B attention kernels (CAPR_BERT_ATTENTION=v1 | v2 | ffma) stay parity-green against the same golden."""
     monkeypatch.setenv("CAPR_BERT_ATTENTION", variant)
     g, rr, model, b = _build("mid")
     scores = rr.test(b).cpu().numpy()
