@@ -81,6 +81,7 @@ SIGNATURES = {
     "capr_parade_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "capr_parade_head": (c_int, [c_void_p, _f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "capr_debug_ffma2_bench": (c_int, [c_int, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
 }
 

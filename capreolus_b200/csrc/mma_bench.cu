@@ -66,3 +66,65 @@ extern "C" int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }
+
+// ---- FFMA2 issue-rate micro-benchmark (debug entry): does the packed fp32 FMA run at the same rate when its scalar operand
+// comes from a uniform register / constant bank (the form PACRR's conv uses) as with a vector-register pair?
+namespace capr {
+__constant__ float c_ffma2_taps[64];
+
+template <int MODE>  // 0: constant-bank scalar broadcast (fma2_bcast), 1: vector-register {w,w} pairs, 2: plain FFMA (two per pair)
+__global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float* __restrict__ gw, float* out, long long* cycles) {
+  float2 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, 1.f);
+  float2 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = make_float2(1.0f + i * 1e-3f, 1.0f - i * 1e-3f);
+  float wreg[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) wreg[t] = gw[t];
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 0) {
+          acc[i] = fma2_bcast(c_ffma2_taps[t], x[i], acc[i]);
+        } else if (MODE == 1) {
+          const float2 ww = make_float2(wreg[t], wreg[t]);
+          unsigned long long rd;
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd)
+              : "l"(*reinterpret_cast<const unsigned long long*>(&ww)), "l"(*reinterpret_cast<const unsigned long long*>(&x[i])),
+                "l"(*reinterpret_cast<const unsigned long long*>(&acc[i])));
+          acc[i] = *reinterpret_cast<float2*>(&rd);
+        } else {
+          acc[i].x = fmaf(wreg[t], x[i].x, acc[i].x);
+          acc[i].y = fmaf(wreg[t], x[i].y, acc[i].y);
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+}  // namespace capr
+
+// cycles[grid]: SM cycles for iters x 16 taps x 8 packed FMAs per thread, 256 threads per CTA (8 warps, 2 per scheduler).
+extern "C" int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long long* cycles, capr_stream_t stream) {
+  CAPR_REQUIRE(mode >= 0 && mode <= 2 && iters > 0 && grid > 0 && scratch && cycles, CAPR_ERR_BAD_SHAPE, "capr_debug_ffma2_bench: bad arguments");
+  float h[64];
+  for (int i = 0; i < 64; ++i) h[i] = 1.0f + 1e-4f * i;
+  CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(capr::c_ffma2_taps, h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CAPR_CHECK_CUDA(cudaMemcpyAsync(scratch, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (mode == 0) capr::ffma2_bench_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
+  else if (mode == 1) capr::ffma2_bench_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
+  else capr::ffma2_bench_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}

@@ -281,6 +281,10 @@ int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int
 /* Debug micro-benchmark (not on any product path): cycles[grid] = best-of-reps SM cycles for n_mma back-to-back
  * tcgen05.mma of shape M x N x 16 (bf16, shared-memory operands) cycling over n_acc accumulators. */
 int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps, int grid, long long* cycles, capr_stream_t stream);
+/* Debug micro-benchmark: cycles[grid] = SM cycles for iters x 128 packed fp32 FMAs per thread (256 threads per CTA) with the
+ * scalar operand from the constant bank (mode 0, the form PACRR's conv uses), from vector registers (mode 1), or as plain FFMA
+ * pairs (mode 2).  scratch: >= 64 + grid*256 floats. */
+int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long long* cycles, capr_stream_t stream);
 
 #ifdef __cplusplus
 }
