@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
         ps.wait_full(s, ub_i);  // also orders the drain warps' id writes of this pair before the reads below
         const int qi = s.qid[(it & 1) * QT + lane];
         drmm_count_slice(half_tile(s, ub_i), HALF_PITCH, pw * 32, min(NT_DOCS, a.D - h * NT_DOCS) - pw * 32, qi,
-                         s.did + (it & 1) * DT + h * NT_DOCS + pw * 32, a, ub, cnt + lane * CNT_PITCH_TC);
+                         s.did + (it & 1) * s.dcap + h * NT_DOCS + pw * 32, a, ub, cnt + lane * CNT_PITCH_TC);
         ps.release(s, ub_i, lane);
       }
       epi_barrier();
@@ -293,8 +293,8 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   CAPR_REQUIRE(hist_type >= 0 && hist_type <= 2, CAPR_ERR_BAD_SHAPE, "%s: histType should be CH, NH or LCH", fn);
   CAPR_REQUIRE(gate_type == 0 || gate_type == 1, CAPR_ERR_BAD_SHAPE, "%s: gateType should be IDF or TV", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
-  CAPR_REQUIRE(D <= DT && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K && nbins + 1 <= MAX_SLOTS_TC, CAPR_ERR_UNSUPPORTED,
-               "%s: needs maxdoclen <= %d, emb dim <= %d, nbins <= %d: use capr_drmm_forward", fn, DT, simtc::MAX_ATOMS * simtc::ATOM_K, MAX_SLOTS_TC - 1);
+  CAPR_REQUIRE(D <= simtc::DEEP_DCAP && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K && nbins + 1 <= MAX_SLOTS_TC, CAPR_ERR_UNSUPPORTED,
+               "%s: needs maxdoclen <= %d, emb dim <= %d, nbins <= %d: use capr_drmm_forward", fn, simtc::DEEP_DCAP, simtc::MAX_ATOMS * simtc::ATOM_K, MAX_SLOTS_TC - 1);
   CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table of %d x %d elements is too large for 32-bit row offsets", fn, V, pitch);
   if (B == 0) return CAPR_OK;
   CAPR_REQUIRE(query && doc && table_hi && table_lo && bin_ub && ffw_w1 && ffw_b1 && ffw_w2 && ffw_b2 && gate_w && out_w && out_b && scores, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
@@ -305,7 +305,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
              simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}};
   const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
   const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
-  a.pr.deep = (atoms >= 3 && !(ring_env && ring_env[0] == '2')) ? 1 : 0;
+  a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
   const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();

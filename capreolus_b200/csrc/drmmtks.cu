@@ -155,7 +155,7 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
   CAPR_REQUIRE(topk <= D, CAPR_ERR_BAD_SHAPE, "%s: topk=%d is out of range for maxdoclen=%d (torch.topk raises in the reference)", fn, topk, D);
   CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 16 and >= E (capr_table_pitch_bf16)", fn, pitch);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
-  CAPR_REQUIRE(D <= DT && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K, CAPR_ERR_UNSUPPORTED, "%s: needs maxdoclen <= %d and emb dim <= %d", fn, DT, simtc::MAX_ATOMS * simtc::ATOM_K);
+  CAPR_REQUIRE(D <= simtc::DEEP_DCAP && pitch <= simtc::MAX_ATOMS * simtc::ATOM_K, CAPR_ERR_UNSUPPORTED, "%s: needs maxdoclen <= %d and emb dim <= %d", fn, simtc::DEEP_DCAP, simtc::MAX_ATOMS * simtc::ATOM_K);
   CAPR_REQUIRE(topk <= 32, CAPR_ERR_UNSUPPORTED, "%s: topk=%d > 32 is not supported", fn, topk);
   CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table of %d x %d elements is too large for 32-bit row offsets", fn, V, pitch);
   if (B == 0) return CAPR_OK;
@@ -165,7 +165,7 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
             topk, idf, ffw_w, ffw_b, gate_w, out_w, out_b, scores, topk_out};
   const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
   const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
-  a.pr.deep = (atoms >= 3 && !(ring_env && ring_env[0] == '2')) ? 1 : 0;
+  a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
   const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);

@@ -43,6 +43,7 @@ constexpr int NT_DOCS = 256;                  // doc rows per MMA (N) = per work
 constexpr int Q_ATOM_BYTES = 64 * 128;        // [q_hi;q_lo] 64 rows x 128 B
 constexpr int D_STAGE_BYTES = NT_DOCS * 128;  // one plane (hi or lo) of 256 doc rows x one 64-element K atom = 32 KB
 constexpr int D_STAGES = 2;                   // ring depth of the default layout
+constexpr int DEEP_DCAP = 1024;               // "deep" layout: doc-id capacity per pair (maxdoclen up to 1024 = four 256-doc units)
 constexpr int MAX_D_STAGES = 3;               // "deep" layout: one query buffer, three doc stages (96 KB of gathers in flight)
 constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
 constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
@@ -62,9 +63,10 @@ struct Smem {
   __device__ __forceinline__ unsigned char* dbuf(int i) const { return d0 + i * D_STAGE_BYTES; }
   float* sim;                 // [SIM_ROWS][SIM_PITCH]
   int* qrow;                  // [QT]   table rows of the pair being gathered (producer)
-  int* drow;                  // [DT]
+  int dcap;                   // doc ids per pair the id arrays below can hold (DT, or DEEP_DCAP in the deep layout)
+  int* drow;                  // [dcap]
   int* qid;                   // [2][QT]   ids of the pair being drained / pooled (epilogue; pipelined mode: by pair parity)
-  int* did;                   // [2][DT]
+  int* did;                   // [2][dcap]
   uint64_t *q_full, *q_empty, *d_full, *d_empty, *acc_full, *acc_empty, *half_full, *half_empty;
   uint32_t* tmem_slot;
   float* extra;               // model-specific scratch
@@ -74,7 +76,7 @@ struct Smem {
 // is latency bound (Little: bytes in flight / loaded L2 latency), so a third 32 KB stage buys more than the second query buffer.
 __host__ __device__ inline size_t smem_bytes(int atoms, size_t extra_bytes, bool deep = false) {
   return 1024 + (size_t)(deep ? 1 : 2) * atoms * Q_ATOM_BYTES + (size_t)(deep ? MAX_D_STAGES : D_STAGES) * D_STAGE_BYTES +
-         (size_t)SIM_ROWS * SIM_PITCH * 4 + (size_t)(3 * QT + 3 * DT) * 4 + 18 * 8 + 16 + extra_bytes;
+         (size_t)SIM_ROWS * SIM_PITCH * 4 + (size_t)(3 * QT + 3 * (deep ? DEEP_DCAP : DT)) * 4 + 18 * 8 + 16 + extra_bytes;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms, bool deep = false) {
@@ -89,11 +91,12 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms, bool deep =
   p += (deep ? MAX_D_STAGES : D_STAGES) * D_STAGE_BYTES;
   s.sim = reinterpret_cast<float*>(p);
   p += SIM_ROWS * SIM_PITCH * 4;
+  s.dcap = deep ? DEEP_DCAP : DT;
   s.qrow = reinterpret_cast<int*>(p);
   s.drow = s.qrow + QT;
-  s.qid = s.drow + DT;
+  s.qid = s.drow + s.dcap;
   s.did = s.qid + 2 * QT;
-  p += (3 * QT + 3 * DT) * 4;
+  p += (3 * QT + 3 * s.dcap) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
   s.q_full = b, s.q_empty = b + 2, s.d_full = b + 4, s.d_empty = b + 4 + MAX_D_STAGES, s.acc_full = b + 4 + 2 * MAX_D_STAGES,
   s.acc_empty = b + 6 + 2 * MAX_D_STAGES;
@@ -187,7 +190,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     const int b = one_qbuf(pr) ? 0 : (it & 1);
     prod_barrier();  // every producer thread is done reading the previous pair's rows
     if (ptid < QT) s.qrow[ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
-    for (int i = ptid; i < DT; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
+    for (int i = ptid; i < halves * NT_DOCS; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
     prod_barrier();
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     tc::mbar_wait(&s.q_empty[b], ((q_phase >> b) & 1) ^ 1);
@@ -373,7 +376,7 @@ __device__ __forceinline__ void drain_loop(const Smem& s, const Problem& pr, uin
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int pp = it & 1;
     int* qid = s.qid + pp * QT;
-    int* did = s.did + pp * DT;
+    int* did = s.did + pp * s.dcap;
     int qi = 0;
     for (int h = 0; h < halves; ++h, ++unit) {
       const int ub = unit & 1;
@@ -385,7 +388,7 @@ __device__ __forceinline__ void drain_loop(const Smem& s, const Problem& pr, uin
         // it-1 when halves == 2 and to pair it-2 when halves == 1).  The writes are ordered before half_full by the
         // barrier below + the hi warps' arrive.
         if (dtid < QT) qid[dtid] = id_as_int(dtid < pr.Q ? pr.q[(size_t)pair * pr.Q + dtid] : 0);
-        for (int i = dtid; i < DT; i += 128) did[i] = id_as_int(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0);
+        for (int i = dtid; i < halves * NT_DOCS; i += 128) did[i] = id_as_int(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0);
         drain_barrier();
         qi = qid[lane];
       }

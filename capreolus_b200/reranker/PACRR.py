@@ -66,7 +66,7 @@ class PACRR_class(nn.Module):
         bs = [ng.conv.bias.detach().contiguous() for ng in self.ngrams]
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         topk = torch.empty((B, Q, len(self.ngrams) * p["kmax"]), dtype=torch.float32, device=q.device) if want_topk else None
-        if common.use_tensor_cores(D, self.embedding_dim) and len(self.ngrams) * p["kmax"] <= 12:
+        if common.use_tensor_cores(D, self.embedding_dim, max_doclen=512) and len(self.ngrams) * p["kmax"] <= 12:
             hi, lo = self._prepared.get_bf16()
             _lib.check(_lib.lib().capr_pacrr_forward_tc(
                 q.data_ptr(), d.data_ptr(), _lib.ptr(idf), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], self.embedding_dim, hi.shape[1],

@@ -20,8 +20,10 @@ ENGINE = os.environ.get("CAPR_SIM_ENGINE", "tc")
 DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only (CAPR_DEBUG_SKIP_*): results invalid
 
 
-def use_tensor_cores(D: int, E: int) -> bool:
-    return ENGINE == "tc" and D <= 512 and E <= 320
+def use_tensor_cores(D: int, E: int, max_doclen: int = 1024) -> bool:
+    """KNRM / DRMM / DRMMTKS pool column-additively over 256-doc units, so their tensor-core kernels take maxdoclen <= 1024 (the
+    reference extractor's default is 800); PACRR needs the whole 512-column tile with its halo (``max_doclen=512``)."""
+    return ENGINE == "tc" and D <= max_doclen and E <= 320
 
 
 def create_emb_layer(weights, non_trainable=True):

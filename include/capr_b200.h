@@ -83,7 +83,7 @@ int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, in
 /* Engine 2 (tensor cores): same contract as capr_knrm_forward (inference outputs only), but the cosine tile is
  * computed by tcgen05.mma from a table stored as two bf16 planes, hi = bf16(e) and lo = bf16(e - hi) of the same
  * L2-normalised rows (capr_table_prepare_bf16; pitch = capr_table_pitch_bf16(E), E rounded up to a multiple of 16), with
- * the three products hi.hi + hi.lo + lo.hi accumulated in fp32.  Limits: D <= 512, pitch <= 320, K <= 16 (else
+ * the three products hi.hi + hi.lo + lo.hi accumulated in fp32.  Limits: D <= 1024, pitch <= 320, K <= 16 (else
  * CAPR_ERR_UNSUPPORTED -> use capr_knrm_forward). */
 int capr_table_pitch_bf16(int E);
 int capr_table_prepare_bf16(const float* emb /*[V,E]*/, int V, int E, void* table_hi /*bf16 [V,pitch]*/,
@@ -110,7 +110,7 @@ int capr_drmm_forward(const int64_t* query, const int64_t* doc, const float* idf
                       int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w, const float* out_w,
                       const float* out_b, float* scores, float* hist_out, capr_stream_t stream);
 
-/* Engine 2 (tensor cores), see capr_knrm_forward_tc.  Limits: D <= 512, pitch <= 320, nbins <= 31. */
+/* Engine 2 (tensor cores), see capr_knrm_forward_tc.  Limits: D <= 1024, pitch <= 320, nbins <= 31. */
 int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D,
                          const void* table_hi, const void* table_lo, int V, int pitch, const float* raw_emb, int E,
                          int nbins, const float* bin_ub, int hist_type, int gate_type, const float* ffw_w1,
@@ -142,7 +142,7 @@ int capr_pacrr_forward_tc(const int64_t* query, const int64_t* doc, const float*
  * (table as bf16 hi/lo planes, capr_table_prepare_bf16).  gateType='TV' is not offered: the reference feeds int64 token
  * ids to a Linear(E,1) there and raises.
  *   ffw_w [1,topk], ffw_b [1], gate_w [1], out_w [1], out_b [1];  idf [B,Q];  topk_out [B,Q,topk] (nullable, descending).
- * Limits: Q <= 32, D <= 512, pitch <= 320, topk <= min(32, D). */
+ * Limits: Q <= 32, D <= 1024, pitch <= 320, topk <= min(32, D). */
 int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc, const float* idf, int B, int Q, int D, const void* table_hi,
                             const void* table_lo, int V, int E, int pitch, int topk, const float* ffw_w, const float* ffw_b,
                             const float* gate_w, const float* out_w, const float* out_b, float* scores, float* topk_out,

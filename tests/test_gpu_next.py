@@ -47,7 +47,8 @@ def test_drmmtks_topk_matches_reference(shape):
     np.testing.assert_allclose(top, g["topk"], atol=3e-6)
 
 
-@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 10, 50, 16)])
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 10, 50, 16),
+                                       (2, 4, 800, 1000, 300), (3, 32, 1000, 2000, 300), (2, 8, 1024, 500, 50)])
 def test_drmmtks_fresh_shapes(B, Q, D, V, E):
     got, want = _fresh("DRMMTKS", "drmmtks_forward", DRMMTKS_CFG["default"], B, Q, D, V, E, seed=61)
     assert rel_err(got, want) < TOL

@@ -192,13 +192,15 @@ def _fresh(cls, oracle_fn, cfg, B, Q, D, V, E, seed, oov=True, **okw):
     return got, want
 
 
-@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 1, 50, 16)])
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 1, 50, 16),
+                                       (150, 32, 800, 3000, 300), (3, 20, 1024, 600, 50), (4, 32, 513, 800, 128)])
 def test_knrm_fresh_shapes(B, Q, D, V, E, engine):
     got, want = _fresh("KNRM", "knrm_forward", KNRM_CFG["default"], B, Q, D, V, E, seed=31)
     assert rel_err(got, want) < TOL
 
 
-@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300)])
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 800, 1000, 300), (5, 17, 1100, 400, 100), (150, 32, 64, 5000, 300),
+                                       (150, 32, 800, 3000, 300), (3, 20, 1024, 600, 50)])
 def test_drmm_fresh_shapes(B, Q, D, V, E, engine):
     got, want = _fresh("DRMM", "drmm_forward", DRMM_CFG["default"], B, Q, D, V, E, seed=41, oov=False, exact_cosines=True)
     assert rel_err(got, want) < TOL
