@@ -200,18 +200,28 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = rsub + 16 * j;  // 0..63
-        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)s.qrow[r & 31] * pr.pitch + sub * 8;
+        const int trow = s.qrow[r & 31];
+        const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)trow * pr.pitch + sub * 8;
         const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
+        const uint32_t nbytes = trow != 0 ? 16u : 0u;  // <pad> / OOV: zero-fill, no global read (see the doc stages below)
         for (int a = 0; a < atoms; ++a)
           if (a + 1 < atoms || sub < last_chunks)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K), "r"(nbytes) : "memory");
       }
     }
     cp_async_arrive_noinc(&s.q_full[b]);
     for (int h = 0; h < halves; ++h) {
+      // Rows of <pad> / OOV tokens (table row 0) are not read at all: cp.async with src-size 0 zero-fills the 16 bytes.  Their
+      // cosine is exactly 0 whatever emb[0] holds (the reference masks them, common.py:149-153), ragged batches only gather
+      // their real tokens, and 148 SMs do not hammer the one L2 line of row 0.
       unsigned off[16];  // element offsets of this thread's 16 rows (V * pitch < 2^31 is checked on the host)
+      unsigned live = 0;  // bit j: row j is a real table row
 #pragma unroll
-      for (int j = 0; j < 16; ++j) off[j] = (unsigned)s.drow[h * NT_DOCS + rsub + 16 * j] * (unsigned)pr.pitch + (unsigned)(sub * 8);
+      for (int j = 0; j < 16; ++j) {
+        const int trow = s.drow[h * NT_DOCS + rsub + 16 * j];
+        off[j] = (unsigned)trow * (unsigned)pr.pitch + (unsigned)(sub * 8);
+        live |= (trow != 0 ? 1u : 0u) << j;
+      }
       for (int a = 0; a < atoms; ++a) {
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
@@ -222,7 +232,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int r = rsub + 16 * j;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
+                           "r"(((live >> j) & 1u) << 4)
+                           : "memory");
             }
           }
           cp_async_arrive_noinc(&s.d_full[d_stage]);
