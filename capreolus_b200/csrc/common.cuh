@@ -33,6 +33,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+// 16-byte copy, or -- live == false -- 16 bytes of zeros without touching global memory (src-size 0).  Used for <pad> / OOV
+// tokens, which all map to table row 0: reading it like any other row makes every SM hammer one L2 line.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool live) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(live ? 16u : 0u) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

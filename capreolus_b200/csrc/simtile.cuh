@@ -85,7 +85,7 @@ __device__ __forceinline__ void issue_query_rows(const SimTile& s, const float* 
   const int qp = pitch + 4;
   for (int i = tid; i < QT * segs; i += NT) {
     int r = i / segs, c = i - r * segs;
-    cp_async16(s.qs + r * qp + c * 4, table + (size_t)s.qrow[r] * pitch + c * 4);
+    cp_async16_zfill(s.qs + r * qp + c * 4, table + (size_t)s.qrow[r] * pitch + c * 4, s.qrow[r] != 0);
   }
 }
 
@@ -105,14 +105,19 @@ __device__ __forceinline__ void sim_tile_gemm(const SimTile& s, const float* __r
   // this thread copies segment `seg` (16 B) of doc rows r0 + 64*i of every chunk
   const int r0 = tid >> 2, seg = tid & 3;
   const float* src[8];
+  unsigned live = 0;  // bit i: row i is a real table row (pad / OOV rows are zero-filled, not read)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) src[i] = table + (size_t)s.drow[r0 + 64 * i] * pitch + seg * 4;
+  for (int i = 0; i < 8; ++i) {
+    const int trow = s.drow[r0 + 64 * i];
+    src[i] = table + (size_t)trow * pitch + seg * 4;
+    live |= (trow != 0 ? 1u : 0u) << i;
+  }
   float* dst0 = s.ds + r0 * DP + seg * 4;
 
   auto issue_chunk = [&](int c) {
     float* dst = dst0 + (c & 1) * (DT * DP);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cp_async16(dst + i * 64 * DP, src[i] + c * KC);
+    for (int i = 0; i < 8; ++i) cp_async16_zfill(dst + i * 64 * DP, src[i] + c * KC, (live >> i) & 1u);
   };
 
   issue_chunk(0);
