@@ -36,7 +36,17 @@ struct DrmmArgs {
   float* scores;
   float* hist_out;
   simtc::Problem pr;  // tensor-core engine only
+  int pool_mode;      // tensor-core engine: DRMM_POOL_* (private byte histograms by default)
 };
+
+constexpr int DRMM_POOL_PRIVATE = 0;  // one byte histogram per (pooling warp, query row): plain LDS/STS, no atomics
+constexpr int DRMM_POOL_ATOMIC = 1;   // shared 32-bit counters per row, integer atomics from the 8 pooling warps (A/B reference)
+constexpr int DRMM_POOL_NOADD = 2;    // profiling only (results invalid): bins computed, nothing counted
+constexpr int DRMM_POOL_SKIP = 3;     // profiling only (results invalid): no pooling work at all
+constexpr int HIST_PITCH_B = 36;      // bytes per private histogram row: word stride 9 is odd, so equal bins of the 32 rows hit 32 banks
+constexpr int HIST_WARP_B = QT * HIST_PITCH_B;  // 1 152 B per pooling warp
+constexpr int HIST_WARPS_IN_SPARE = 6;           // 6 912 B behind the half tiles; warps 6, 7 + bounds + z live in the extra region
+constexpr size_t DRMM_TC_EXTRA_BYTES = (size_t)(simtc::POOL_WARPS - HIST_WARPS_IN_SPARE) * HIST_WARP_B + (MAX_SLOTS_TC + QT) * sizeof(float);
 
 struct BlockSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -91,11 +101,16 @@ __device__ __forceinline__ void drmm_count_tile(const float* sim, const int* qid
 }
 
 // Tensor-core engine: lane = query row, warp = a 32-column slice of the half tile (the one-row-per-lane float4 reads are
-// conflict-free, the doc ids of the slice are warp-uniform broadcasts, so the padding test is a uniform branch).  All 8
-// slices add into the same per-row counters with shared-memory integer atomics: integer adds commute, so the result is
-// deterministic; the odd row stride puts equal bins of different rows in different banks.
+// conflict-free, the doc ids of the slice are warp-uniform broadcasts).  Counting (MODE): by default each (pooling warp,
+// row) owns a byte histogram, so the lane is the only writer of its counters and plain loads / stores do; the A/B mode
+// adds into one per-row counter array with shared-memory integer atomics (integer adds commute: deterministic either
+// way).  Odd word strides put equal bins of different rows in different banks.  The pooling is latency-bound, not
+// issue-bound: computing the four bins of a float4 branch-free (overlapping their F2I -> LDS -> compare chains) took the
+// kernel from 9.4 M to 10.3 M pairs/s; packing the counters into registers (no shared traffic, +16 ALU ops per cosine) or
+// moving the producers to their own sub-partition both lost.
+template <int MODE>
 __device__ __forceinline__ void drmm_count_slice(const float* tile, int pitch, int col0, int nvalid, int qi, const int* did_slice,
-                                                 const DrmmArgs& a, const float* ub, int* cnt_row) {
+                                                 const DrmmArgs& a, const float* ub, int* cnt_row, unsigned char* hist_row, int& sink) {
   const float guess_scale = 0.5f * (float)a.nbins;
   const float4* row = reinterpret_cast<const float4*>(tile + (threadIdx.x & 31) * pitch + col0);
   const int4* dids = reinterpret_cast<const int4*>(did_slice);
@@ -105,32 +120,69 @@ __device__ __forceinline__ void drmm_count_slice(const float* tile, int pitch, i
     const int4 d4 = dids[g];
     const float vv[4] = {x.x, x.y, x.z, x.w};
     const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    // the four bins are computed branch-free so that their dependent chains (F2I -> bound lookups -> compares) overlap
+    int bin[4];
+    bool exact[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (g * 4 + j >= nvalid || dd[j] == 0) continue;  // warp-uniform.  Padded columns are pushed to +1e7: no bin (DRMM.py:59)
       const float v = vv[j];
+      const bool real = g * 4 + j < nvalid && dd[j] != 0;  // padded columns are pushed to +1e7: no bin (DRMM.py:59)
       // same binning as drmm_count_tile: arithmetic guess, one comparison on each side against the exact fp32 bounds
       const int g0 = max(0, min((int)floorf((v + 1.0f) * guess_scale), a.nbins - 1));
       const float hi = ub[g0];
       const float lo = ub[max(g0 - 1, 0)];
       int b = g0 + ((v >= hi) ? 1 : 0) - ((g0 > 0 && v < lo) ? 1 : 0);
       if (v == 1.0f && qi > 0 && qi == dd[j]) b = a.nbins - 1;  // identical in-vocabulary tokens (see drmm_count_tile)
-      if (b < a.nbins) atomicAdd(cnt_row + b, 1);
-      if (v > 0.999f && v < 1.001f) atomicAdd(cnt_row + a.nbins, 1);  // DRMM.py:66
+      bin[j] = real ? b : a.nbins;                              // nbins = "no bin" (also v >= 1.0)
+      exact[j] = real && v > 0.999f && v < 1.001f;              // DRMM.py:66
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = bin[j];
+      if (MODE == DRMM_POOL_PRIVATE) {
+        // this lane's own row of this warp's own histogram: at most 32 columns x 4 units = 128 increments per pair (fits a byte)
+        if (b < a.nbins) hist_row[b] = (unsigned char)(hist_row[b] + 1);
+        if (exact[j]) hist_row[a.nbins] = (unsigned char)(hist_row[a.nbins] + 1);
+      } else if (MODE == DRMM_POOL_ATOMIC) {
+        if (b < a.nbins) atomicAdd(cnt_row + b, 1);
+        if (exact[j]) atomicAdd(cnt_row + a.nbins, 1);
+      } else {
+        sink += b;
+      }
     }
   }
 }
 
 // counts -> +1 -> CH/NH/LCH -> 2-layer tanh feed-forward per query row -> softmax term gate -> score
-template <int SLOTS, class Sync>
-__device__ __forceinline__ void drmm_finish(const DrmmArgs& a, int pair, const int* cnt, float* z, int warp, int lane, Sync sync) {
+// Counter accessors for drmm_finish: a [row][SLOTS] int array, or the sum of the 8 private byte histograms.
+template <int SLOTS>
+struct ArrayCounts {
+  const int* cnt;
+  __device__ __forceinline__ int operator()(int qrow, int slot) const { return cnt[qrow * SLOTS + slot]; }
+};
+struct PrivateCounts {
+  const unsigned char* spare;  // pooling warps 0..HIST_WARPS_IN_SPARE-1
+  const unsigned char* extra;  // the rest
+  __device__ __forceinline__ const unsigned char* warp_hist(int pw) const {
+    return pw < HIST_WARPS_IN_SPARE ? spare + pw * HIST_WARP_B : extra + (pw - HIST_WARPS_IN_SPARE) * HIST_WARP_B;
+  }
+  __device__ __forceinline__ int operator()(int qrow, int slot) const {
+    int c = 0;
+#pragma unroll
+    for (int pw = 0; pw < simtc::POOL_WARPS; ++pw) c += warp_hist(pw)[qrow * HIST_PITCH_B + slot];
+    return c;
+  }
+};
+
+template <int SLOTS, class Counts, class Sync>
+__device__ __forceinline__ void drmm_finish(const DrmmArgs& a, int pair, const Counts cnt, float* z, int warp, int lane, Sync sync) {
   const int nslots = a.nbins + 1;
   const long long* qids = a.q + (size_t)pair * a.Q;
   for (int r = 0; r < 4; ++r) {
     const int qrow = warp * 4 + r;
     if (qrow >= a.Q) continue;  // warp-uniform
-    float h0 = lane < nslots ? (float)(cnt[qrow * SLOTS + lane] + 1) : 0.f;
-    float h1 = (SLOTS > 32 && lane + 32 < nslots) ? (float)(cnt[qrow * SLOTS + (lane + 32) % SLOTS] + 1) : 0.f;
+    float h0 = lane < nslots ? (float)(cnt(qrow, lane) + 1) : 0.f;
+    float h1 = (SLOTS > 32 && lane + 32 < nslots) ? (float)(cnt(qrow, (lane + 32) % SLOTS) + 1) : 0.f;
     if (a.hist_type == CAPR_DRMM_NH) {
       const float tot = warp_sum(h0 + h1);
       h0 /= tot;
@@ -199,22 +251,29 @@ __global__ void __launch_bounds__(NT, 1) drmm_kernel(const DrmmArgs a) {
       drmm_count_tile<MAX_SLOTS, SIM_PITCH, DT>(s.sim, s.qid, s.did, min(DT, a.D - d0), a, ub, cnt, warp, lane);
       __syncthreads();
     }
-    drmm_finish<MAX_SLOTS>(a, pair, cnt, z, warp, lane, BlockSync());
+    drmm_finish<MAX_SLOTS>(a, pair, ArrayCounts<MAX_SLOTS>{cnt}, z, warp, lane, BlockSync());
     __syncthreads();  // z / cnt are rewritten by the next pair
   }
 }
 
-// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh, pipelined epilogue); same counting + finish code on the 8
-// pooling warps, one half tile (256 docs) at a time.
+// Engine 2: cosine tile from the tcgen05 producer (simtc.cuh, pipelined epilogue); counting + finish on the 8 pooling
+// warps, one half tile (256 docs) at a time.  MODE = DRMM_POOL_*: by default every (pooling warp, query row) owns a byte
+// histogram (the lane is the only writer of its row: plain loads and stores), summed over the 8 warps by drmm_finish.
+template <int MODE>
 __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const DrmmArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
+  constexpr bool PRIV = MODE != DRMM_POOL_ATOMIC;
   static_assert((QT * CNT_PITCH_TC + MAX_SLOTS_TC + QT) <= SPARE_FLOATS, "DRMM scratch must fit behind the two half tiles");
-  int* cnt = reinterpret_cast<int*>(spare_scratch(s));            // [QT][CNT_PITCH_TC]
-  float* ub = reinterpret_cast<float*>(cnt + QT * CNT_PITCH_TC);  // [MAX_SLOTS_TC]
-  float* z = ub + MAX_SLOTS_TC;                                   // [QT]
+  static_assert(HIST_WARPS_IN_SPARE * HIST_WARP_B + (MAX_SLOTS_TC + QT) * 4 <= SPARE_FLOATS * 4, "private histograms must fit behind the two half tiles");
+  static_assert(MAX_SLOTS_TC <= HIST_PITCH_B && HIST_PITCH_B % 4 == 0, "histogram row holds every slot, word-aligned");
+  unsigned char* spare = reinterpret_cast<unsigned char*>(spare_scratch(s));
+  unsigned char* extra = reinterpret_cast<unsigned char*>(s.extra);  // DRMM_TC_EXTRA_BYTES
+  int* cnt = reinterpret_cast<int*>(spare);                          // atomic mode: [QT][CNT_PITCH_TC]
+  float* ub = PRIV ? reinterpret_cast<float*>(spare + HIST_WARPS_IN_SPARE * HIST_WARP_B) : reinterpret_cast<float*>(cnt + QT * CNT_PITCH_TC);  // [MAX_SLOTS_TC]
+  float* z = ub + MAX_SLOTS_TC;                                      // [QT]
   const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
   if (is_producer_warp(warp)) {
     producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
@@ -226,23 +285,36 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
     const int pw = pool_index(warp), ptid = pw * 32 + lane;
     const int halves = halves_of(a.pr);
     if (ptid < a.nbins) ub[ptid] = a.bin_ub[ptid];
+    const PrivateCounts priv{spare, extra};
+    unsigned char* hist_row = const_cast<unsigned char*>(priv.warp_hist(pw)) + lane * HIST_PITCH_B;
     PoolSync ps;
-    int unit = 0, it = 0;
+    int unit = 0, it = 0, sink = 0;
     for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, ++it) {
-      for (int i = ptid; i < QT * CNT_PITCH_TC; i += POOL_WARPS * 32) cnt[i] = 0;
+      if (PRIV) {
+#pragma unroll
+        for (int w = 0; w < HIST_PITCH_B / 4; ++w) reinterpret_cast<uint32_t*>(hist_row)[w] = 0u;
+      } else {
+        for (int i = ptid; i < QT * CNT_PITCH_TC; i += POOL_WARPS * 32) cnt[i] = 0;
+      }
       epi_barrier();  // the 8 pooling warps: counters (and, first time, the bounds) are in place
       for (int h = 0; h < halves; ++h, ++unit) {
         const int ub_i = unit & 1;
         ps.wait_full(s, ub_i);  // also orders the drain warps' id writes of this pair before the reads below
-        const int qi = s.qid[(it & 1) * QT + lane];
-        drmm_count_slice(half_tile(s, ub_i), HALF_PITCH, pw * 32, min(NT_DOCS, a.D - h * NT_DOCS) - pw * 32, qi,
-                         s.did + (it & 1) * s.dcap + h * NT_DOCS + pw * 32, a, ub, cnt + lane * CNT_PITCH_TC);
+        if (MODE != DRMM_POOL_SKIP) {
+          const int qi = s.qid[(it & 1) * QT + lane];
+          drmm_count_slice<MODE>(half_tile(s, ub_i), HALF_PITCH, pw * 32, min(NT_DOCS, a.D - h * NT_DOCS) - pw * 32, qi,
+                                 s.did + (it & 1) * s.dcap + h * NT_DOCS + pw * 32, a, ub, cnt + lane * CNT_PITCH_TC, hist_row, sink);
+        }
         ps.release(s, ub_i, lane);
       }
       epi_barrier();
-      drmm_finish<CNT_PITCH_TC>(a, pair, cnt, z, pw, lane, EpiSync());
-      epi_barrier();  // z / cnt are rewritten by the next pair
+      if (PRIV)
+        drmm_finish<HIST_PITCH_B>(a, pair, priv, z, pw, lane, EpiSync());
+      else
+        drmm_finish<CNT_PITCH_TC>(a, pair, ArrayCounts<CNT_PITCH_TC>{cnt}, z, pw, lane, EpiSync());
+      epi_barrier();  // z / the counters are rewritten by the next pair
     }
+    if (MODE == DRMM_POOL_NOADD && sink == 0x7fffffff) z[0] = 1.f;  // keeps the profiling-only mode's bin arithmetic alive
   }
   teardown(s, tmem_base, tid, MMA_WARP_PIPE);
 }
@@ -271,7 +343,7 @@ extern "C" int capr_drmm_forward(const int64_t* query, const int64_t* doc, const
   CAPR_REQUIRE(nbins + 1 <= MAX_SLOTS, CAPR_ERR_UNSUPPORTED, "%s: nbins=%d > %d is not supported", fn, nbins, MAX_SLOTS - 1);
   if (B == 0) return CAPR_OK;
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
-             table, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out, simtc::Problem{}};
+             table, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out, simtc::Problem{}, 0};
   size_t smem = sim_tile_bytes(pitch) + (size_t)QT * MAX_SLOTS * sizeof(int) + (MAX_SLOTS + QT) * sizeof(float);
   CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
@@ -302,15 +374,30 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   CAPR_REQUIRE(gate_type != CAPR_DRMM_GATE_TV || raw_emb, CAPR_ERR_BAD_POINTER, "%s: TV gate needs the raw embedding table", fn);
   DrmmArgs a{(const long long*)query, (const long long*)doc, idf, B, Q, D, V, pitch, E, nbins, hist_type, gate_type, nodes,
              nullptr, raw_emb, bin_ub, ffw_w1, ffw_b1, ffw_w2, ffw_b2, gate_w, out_w, out_b, scores, hist_out,
-             simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}};
+             simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, E, 0}, 0};
   const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
   const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
   a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
-  const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
-  CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = simtc::smem_bytes(atoms, DRMM_TC_EXTRA_BYTES, a.pr.deep != 0);
+  CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory needed", fn, smem);
+  // CAPR_DRMM_POOL = atomic | noadd | skip selects the A/B reference and the profiling-only ablations (results invalid for the last two)
+  const char* pool_env = getenv("CAPR_DRMM_POOL");
+  a.pool_mode = !pool_env ? DRMM_POOL_PRIVATE : pool_env[0] == 'a' ? DRMM_POOL_ATOMIC : pool_env[0] == 'n' ? DRMM_POOL_NOADD : pool_env[0] == 's' ? DRMM_POOL_SKIP : DRMM_POOL_PRIVATE;
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
-  drmm_tc_kernel<<<B < sms ? B : sms, simtc::THREADS_PIPE, smem, (cudaStream_t)stream>>>(a);
+  const int grid = B < sms ? B : sms;
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, simtc::THREADS_PIPE, smem, (cudaStream_t)stream>>>(a);
+    return cudaSuccess;
+  };
+  switch (a.pool_mode) {
+    case DRMM_POOL_ATOMIC: CAPR_CHECK_CUDA(launch(drmm_tc_kernel<DRMM_POOL_ATOMIC>)); break;
+    case DRMM_POOL_NOADD: CAPR_CHECK_CUDA(launch(drmm_tc_kernel<DRMM_POOL_NOADD>)); break;
+    case DRMM_POOL_SKIP: CAPR_CHECK_CUDA(launch(drmm_tc_kernel<DRMM_POOL_SKIP>)); break;
+    default: CAPR_CHECK_CUDA(launch(drmm_tc_kernel<DRMM_POOL_PRIVATE>)); break;
+  }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }
