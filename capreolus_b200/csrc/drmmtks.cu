@@ -63,13 +63,17 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmmtks_tc_kernel(cons
           const float v[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (g * 4 + j < nvalid && v[j] > t[T - 1]) {
-              t[T - 1] = v[j];
+            // sorted insert without a serial bubble: every slot is rebuilt from the OLD list, t'[i] = max(min(t[i-1], v), t[i])
+            // (v <= t[i]: unchanged; t[i] < v <= t[i-1]: v lands here; v > t[i-1]: the old t[i-1] shifts down).  Branch-free
+            // and two operations deep, so consecutive cosines overlap; columns past the end enter as -inf (no effect).
+            const float nv = (g * 4 + j < nvalid) ? v[j] : -INFINITY;
+            float prev = t[0];
+            t[0] = fmaxf(prev, nv);
 #pragma unroll
-              for (int i = T - 1; i > 0; --i) {  // bubble the newcomer up
-                const float hi = fmaxf(t[i - 1], t[i]), lo = fminf(t[i - 1], t[i]);
-                t[i - 1] = hi, t[i] = lo;
-              }
+            for (int i = 1; i < T; ++i) {
+              const float cur = t[i];
+              t[i] = fmaxf(fminf(prev, nv), cur);
+              prev = cur;
             }
           }
         }

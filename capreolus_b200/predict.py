@@ -20,10 +20,15 @@ class PinnedBatch:
 
 
 class PipelinedPredictor:
-    """Double-buffered H2D / score / D2H pipeline around ``reranker.test``."""
+    """Double-buffered H2D / score / D2H pipeline around ``reranker.test``.
 
-    def __init__(self, reranker, device, chunk: int = 16384):
-        self.reranker, self.device, self.chunk = reranker, torch.device(device), int(chunk)
+    ``ramp``: the first copy cannot overlap anything, so the schedule starts with chunks of ``chunk/8, chunk/4, chunk/2``
+    items (the exposed copy shrinks 8x) and then continues with full chunks."""
+
+    def __init__(self, reranker, device, chunk: int = 16384, ramp: bool = True):
+        self.reranker, self.device, self.chunk, self.ramp = reranker, torch.device(device), int(chunk), bool(ramp)
+        if self.chunk <= 0:
+            raise ValueError("PipelinedPredictor: chunk must be positive")
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._bufs = None
         self._out_host = None
@@ -38,17 +43,28 @@ class PipelinedPredictor:
             self._out_host = torch.empty(pb.n, dtype=torch.float32).pin_memory()
         return self._bufs[1]
 
+    def schedule(self, n: int) -> list:
+        """``[(lo, hi), ...]`` covering ``range(n)``: ramp-up chunks first (if enabled), then full chunks."""
+        sizes, lo, out = ([self.chunk // 8, self.chunk // 4, self.chunk // 2] if self.ramp else []), 0, []
+        for sz in sizes:
+            if sz > 0 and lo + sz < n:
+                out.append((lo, lo + sz))
+                lo += sz
+        while lo < n:
+            out.append((lo, min(n, lo + self.chunk)))
+            lo += self.chunk
+        return out
+
     @torch.no_grad()
     def predict(self, pb: PinnedBatch) -> torch.Tensor:
         """Scores for every item of ``pb`` as a pinned host fp32 tensor ``[n]`` (valid after this call returns)."""
         bufs = self._buffers(pb)
         main = torch.cuda.current_stream(self.device)
-        n_chunks = (pb.n + self.chunk - 1) // self.chunk
-        copied = [torch.cuda.Event() for _ in range(n_chunks)]
-        scored = [torch.cuda.Event() for _ in range(n_chunks)]
+        spans = self.schedule(pb.n)
+        copied = [torch.cuda.Event() for _ in spans]
+        scored = [torch.cuda.Event() for _ in spans]
         self.copy_stream.wait_stream(main)
-        for i in range(n_chunks):
-            lo, hi = i * self.chunk, min(pb.n, (i + 1) * self.chunk)
+        for i, (lo, hi) in enumerate(spans):
             buf = bufs[i % 2]
             with torch.cuda.stream(self.copy_stream):
                 if i >= 2:

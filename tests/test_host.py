@@ -216,6 +216,23 @@ def test_packed_id_store_layout_and_validation():
         PackedIdStore(["a"], [1, 2], [0, 2], idf=[1.0])
 
 
+@pytest.mark.parametrize("n", [0, 1, 5, 777, 6216, 100_000])
+@pytest.mark.parametrize("ramp", [True, False])
+def test_pipelined_predictor_schedule_covers_every_item_once(n, ramp):
+    """Chunk schedule of the host predict loop (`predict.PipelinedPredictor.schedule`): contiguous, complete, bounded by
+    `chunk`; with `ramp` the first chunk is at most chunk/8 so the only non-overlapped H2D copy is short."""
+    from capreolus_b200.predict import PipelinedPredictor
+
+    p = PipelinedPredictor.__new__(PipelinedPredictor)  # no CUDA stream needed for the schedule
+    p.chunk, p.ramp = 6216, ramp
+    spans = p.schedule(n)
+    assert [lo for lo, _ in spans] == [0] * bool(spans) + [hi for _, hi in spans[:-1]]
+    assert (spans[-1][1] if spans else 0) == n
+    assert all(0 < hi - lo <= p.chunk for lo, hi in spans)
+    if ramp and n > p.chunk:
+        assert spans[0][1] - spans[0][0] == p.chunk // 8
+
+
 def test_write_trec_run_matches_the_reference_format(tmp_path):
     """capreolus/searcher/__init__.py:48-58: qids in int order, docs by score descending (stable), 'qid Q0 docid rank score capreolus'."""
     from capreolus_b200.predict import write_trec_run
