@@ -140,7 +140,8 @@ class PairAssembler:
         self.queries, self.docs = queries.to(self.device), docs.to(self.device)
         self.Q, self.D = int(maxqlen), int(maxdoclen)
 
-    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None) -> dict:
+    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None, rows: int | None = None) -> dict:
+        """Fill ``out`` (allocated when ``None``; ``rows`` = capacity to allocate, default ``len(qidx)``) with the padded rows."""
         from capreolus_b200 import _lib
 
         _lib.require_cuda(qidx, didx)
@@ -148,9 +149,12 @@ class PairAssembler:
             raise ValueError("PairAssembler.assemble: index vectors must be int32")
         n = qidx.shape[0]
         if out is None:
-            out = {"query": torch.empty((n, self.Q), dtype=torch.int64, device=self.device),
-                   "posdoc": torch.empty((n, self.D), dtype=torch.int64, device=self.device),
-                   "query_idf": torch.empty((n, self.Q), dtype=torch.float32, device=self.device)}
+            cap = n if rows is None else int(rows)
+            out = {"query": torch.empty((cap, self.Q), dtype=torch.int64, device=self.device),
+                   "posdoc": torch.empty((cap, self.D), dtype=torch.int64, device=self.device),
+                   "query_idf": torch.empty((cap, self.Q), dtype=torch.float32, device=self.device)}
+        if n == 0:
+            return out
         q, d = self.queries, self.docs
         _lib.check(_lib.lib().capr_assemble_pairs(
             q.flat.data_ptr(), q.offsets.data_ptr(), len(q), d.flat.data_ptr(), d.offsets.data_ptr(), len(d), _lib.ptr(q.idf),
@@ -172,7 +176,8 @@ class BertPairAssembler:
         self.passagelen, self.stride, self.padq = int(passagelen), int(stride), bool(padq)
         self.cls_id, self.sep_id, self.pad_id = int(cls_id), int(sep_id), int(pad_id)
 
-    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None) -> dict:
+    def assemble(self, qidx: torch.Tensor, didx: torch.Tensor, out: dict | None = None, rows: int | None = None) -> dict:
+        """Fill ``out`` (allocated when ``None``; ``rows`` = capacity to allocate, default ``len(qidx)``) with the passage rows."""
         from capreolus_b200 import _lib
 
         _lib.require_cuda(qidx, didx)
@@ -180,7 +185,10 @@ class BertPairAssembler:
             raise ValueError("BertPairAssembler.assemble: index vectors must be int32")
         n = qidx.shape[0]
         if out is None:
-            out = {k: torch.empty((n, self.P, self.L), dtype=torch.int64, device=self.device) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+            cap = n if rows is None else int(rows)
+            out = {k: torch.empty((cap, self.P, self.L), dtype=torch.int64, device=self.device) for k in ("pos_bert_input", "pos_mask", "pos_seg")}
+        if n == 0:
+            return out
         q, d = self.queries, self.docs
         _lib.check(_lib.lib().capr_assemble_bert_pairs(
             q.flat.data_ptr(), q.offsets.data_ptr(), len(q), d.flat.data_ptr(), d.offsets.data_ptr(), len(d), qidx.contiguous().data_ptr(),
@@ -222,6 +230,7 @@ class RunPredictor:
         self.assembler, self.chunk = assembler, int(chunk)
         self.device = assembler.device
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._bufs = None
 
     @torch.no_grad()
     def score_indices(self, reranker, qidx_host: torch.Tensor, didx_host: torch.Tensor) -> torch.Tensor:
@@ -235,13 +244,15 @@ class RunPredictor:
             dd = didx_host.to(self.device, non_blocking=True)
         main.wait_stream(self.copy_stream)
         qd.record_stream(main), dd.record_stream(main)
-        bufs = None
+        # one set of assembly buffers of the full chunk size, reused by every chunk and every call (a ragged last chunk takes
+        # a leading view: no allocator traffic inside the loop)
+        if self._bufs is None:
+            self._bufs = self.assembler.assemble(qd[:0], dd[:0], None, rows=self.chunk)
         for lo in range(0, n, self.chunk):
             hi = min(n, lo + self.chunk)
-            if bufs is not None and next(iter(bufs.values())).shape[0] != hi - lo:
-                bufs = None
-            bufs = self.assembler.assemble(qd[lo:hi], dd[lo:hi], bufs)
-            scores[lo:hi] = reranker.test(bufs).view(-1)
+            view = {k: v[: hi - lo] for k, v in self._bufs.items()}
+            self.assembler.assemble(qd[lo:hi], dd[lo:hi], view)
+            scores[lo:hi] = reranker.test(view).view(-1)
         return scores
 
     @torch.no_grad()
