@@ -318,7 +318,7 @@ def main():
             names = list(range(n))
             qs = PackedIdStore(names, t["query"].reshape(-1).numpy(), np.arange(n + 1, dtype=np.int64) * Q, idf=t["query_idf"].reshape(-1).numpy())
             ds = PackedIdStore(names, t["posdoc"].reshape(-1).numpy(), np.arange(n + 1, dtype=np.int64) * D)
-            rp = RunPredictor(PairAssembler(qs, ds, Q, D, dev), chunk=int(os.environ.get("CAPR_BENCH_PACKED_CHUNK", args.chunk)))
+            rp = RunPredictor(PairAssembler(qs, ds, Q, D, dev), chunk=int(os.environ.get("CAPR_BENCH_PACKED_CHUNK", 4 * args.chunk)))  # no bulk H2D to hide: fewer, larger chunks keep the host launch loop off the critical path
             idx = torch.arange(n, dtype=torch.int32).pin_memory()
             host_scores = torch.empty(n, dtype=torch.float32).pin_memory()
             for _ in range(2):
