@@ -186,12 +186,32 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
   uint32_t q_phase = 0, d_phase = 0;  // q_phase: one bit per buffer
   int d_stage = 0, it = 0;
   const int nst = ring_depth(pr);
+  // The ids of the NEXT pair are fetched into registers while this pair's gathers are being issued: the ids stream from
+  // HBM (one use each), and a load -> barrier -> first gather chain at the top of every pair would leave the ring
+  // draining for a DRAM round trip.
+  constexpr int IDS_PER_THREAD = DEEP_DCAP / PROD_THREADS;  // 8 doc ids per producer thread at most
+  long long q_next = 0, d_next[IDS_PER_THREAD];
+  auto fetch_ids = [&](int pair) {
+    const bool have = pair < pr.B;
+    q_next = (have && ptid < pr.Q) ? pr.q[(size_t)pair * pr.Q + ptid] : 0;  // ptid < Q <= QT
+#pragma unroll
+    for (int j = 0; j < IDS_PER_THREAD; ++j) {
+      const int i = ptid + PROD_THREADS * j;
+      d_next[j] = (have && i < pr.D) ? pr.d[(size_t)pair * pr.D + i] : 0;
+    }
+  };
+  fetch_ids(blockIdx.x);
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = one_qbuf(pr) ? 0 : (it & 1);
     prod_barrier();  // every producer thread is done reading the previous pair's rows
-    if (ptid < QT) s.qrow[ptid] = table_row(ptid < pr.Q ? pr.q[(size_t)pair * pr.Q + ptid] : 0, pr.V);
-    for (int i = ptid; i < halves * NT_DOCS; i += PROD_THREADS) s.drow[i] = table_row(i < pr.D ? pr.d[(size_t)pair * pr.D + i] : 0, pr.V);
+    if (ptid < QT) s.qrow[ptid] = table_row(q_next, pr.V);
+#pragma unroll
+    for (int j = 0; j < IDS_PER_THREAD; ++j) {
+      const int i = ptid + PROD_THREADS * j;
+      if (i < halves * NT_DOCS) s.drow[i] = table_row(d_next[j], pr.V);
+    }
     prod_barrier();
+    fetch_ids(pair + gridDim.x);
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     tc::mbar_wait(&s.q_empty[b], ((q_phase >> b) & 1) ^ 1);
     q_phase ^= 1u << b;
