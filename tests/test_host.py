@@ -233,6 +233,50 @@ def test_pipelined_predictor_schedule_covers_every_item_once(n, ramp):
         assert spans[0][1] - spans[0][0] == p.chunk // 8
 
 
+@pytest.mark.parametrize("k", [1, 3, 10])
+def test_emulated_topk_insert_equals_torch_topk(k):
+    """The branch-free sorted insert of drmmtks.cu (tests/emulate.py) keeps exactly torch.topk's multiset, duplicates included."""
+    from emulate import emulated_topk_insert
+
+    rng = np.random.default_rng(k)
+    for trial in range(20):
+        n = int(rng.integers(k, 80))
+        v = rng.standard_normal(n).astype(np.float32)
+        v[rng.integers(0, n, size=n // 3)] = 0.0  # zeros of padded columns compete (DRMMTKS over the zero-padded matrix)
+        if trial % 4 == 0:
+            v[rng.integers(0, n, size=3)] = 1.0  # several exact matches
+        want = torch.topk(torch.from_numpy(v), k).values.numpy()
+        assert np.array_equal(emulated_topk_insert(v, k), want)
+
+
+def test_emulated_drmm_counts_equal_the_reference_histogram():
+    """The one-pass binning of drmm.cu (tests/emulate.py) equals the reference's `sim < ub_i` counting + differencing
+    (`DRMM.py:55-70`) on cosines that include bin edges, exact matches, pads and values >= 1."""
+    from emulate import emulated_drmm_counts
+
+    nbins = 29
+    rng = np.random.default_rng(7)
+    ub = torch.linspace(-1, 1, nbins + 1)[1:]
+    for trial in range(10):
+        D = 96
+        sim = torch.from_numpy(rng.uniform(-1.0, 1.0, size=D).astype(np.float32))
+        sim[:nbins] = ub[:nbins]                                   # exactly on every upper bound
+        sim[nbins:2 * nbins - 1] = torch.nextafter(ub[:nbins - 1], torch.tensor(-2.0))  # one ulp below the bounds
+        sim[60] = 0.9995                                           # inside the exact slot, below 1.0
+        dids = rng.integers(1, 1000, size=D)
+        dids[70:76] = 0                                            # pads: no bin
+        sim[70:76] = 0.0
+        want = torch.zeros(nbins + 1)
+        real = torch.from_numpy(dids != 0)
+        masked = torch.where(real, sim, torch.full_like(sim, 1e7))  # DRMM.py:59
+        cum = torch.stack([(masked < ub[i]).sum() for i in range(nbins)]).float()
+        want[0] = cum[0]
+        want[1:nbins] = cum[1:] - cum[:-1]
+        want[nbins] = ((masked > 0.999) & (masked < 1.001)).sum()
+        got = emulated_drmm_counts(sim.numpy(), dids, qid=5, nbins=nbins)
+        assert np.array_equal(got, want.numpy().astype(np.int64)), trial
+
+
 def test_write_trec_run_matches_the_reference_format(tmp_path):
     """capreolus/searcher/__init__.py:48-58: qids in int order, docs by score descending (stable), 'qid Q0 docid rank score capreolus'."""
     from capreolus_b200.predict import write_trec_run
