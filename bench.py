@@ -369,7 +369,9 @@ def main():
                 traffic = json.loads(tf.read_text()).get("dram_bytes_per_pair", 0) * n or None
             roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": traffic,
                     "peak_source": pk["src"] + " hbm_gbs", "kernel": TOP_KERNEL[args.model], "kernel_ms_per_launch": kernel_ms,
-                    "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "pairs_per_launch": n}
+                    "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "pairs_per_launch": n,
+                    "note": "achieved = logical gather bytes (SURVEY.md 8d: ids + 544 gathered fp32 rows + score) / kernel time; the 36 MB table is "
+                            "L2-resident, so the gather is L2->SM traffic and frac can exceed 1; `traffic` is the DRAM bytes ncu measured per launch"}
             launches = args.steps * (1 if args.model != "convknrm" else 13 * ((n + 4095) // 4096))  # ConvKNRM: zero row, 2 rep kernels, 9 views, combine per chunk
             workload = (f"{MODELS[args.model]} forward, {n} synthetic pairs per GPU per step (BASELINE.json configs[1]), |q|={Q} |d|={D} vocab={V} "
                         f"emb={E}, zipf ids, random-init weights")
