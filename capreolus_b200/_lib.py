@@ -13,10 +13,14 @@ from pathlib import Path
 
 LIB_NAME = "libcapr_b200.so"
 LIB_PATH = Path(os.environ.get("CAPR_B200_LIB", Path(__file__).resolve().parent / LIB_NAME))
+#: debug build of the same sources (-DCAPR_DEBUG_BUILD) + the micro-benchmarks; loaded only by dbg_lib() (tests, scripts, the
+#: L2-gather roofline probe of bench.py).  Setting CAPR_B200_LIB to it makes the profiling switches (CAPR_DEBUG_FLAGS ...) live.
+DBG_LIB_PATH = Path(__file__).resolve().parent / "libcapr_b200_dbg.so"
 
 CAPR_OK, BAD_SHAPE, BAD_POINTER, UNSUPPORTED, CUDA_ERROR, NO_DEVICE = 0, -1, -2, -3, -4, -5
 
 _lib = None
+_dbg_lib = None
 
 _f32p, _i64p = c_void_p, c_void_p  # device pointers travel as plain addresses (tensor.data_ptr())
 
@@ -66,6 +70,7 @@ SIGNATURES = {
                                     _i64p, _i64p, _f32p, c_void_p]),
     "capr_assemble_bert_pairs": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, _i64p, _i64p, _i64p, c_void_p]),
+    "capr_widen_ids": (c_int, [c_void_p, c_int, c_size_t, _i64p, c_void_p]),
     "capr_rank_by_query": (c_int, [_f32p, c_void_p, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
     "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),
@@ -80,6 +85,10 @@ SIGNATURES = {
                                    c_int, _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_parade_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "capr_parade_head": (c_int, [c_void_p, _f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
+}
+
+#: exported by libcapr_b200_dbg.so only (include/capr_b200.h, `#ifdef CAPR_DEBUG_BUILD`)
+DEBUG_SIGNATURES = {
     "capr_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "capr_debug_ffma2_bench": (c_int, [c_int, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
@@ -109,11 +118,25 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def check(rc: int) -> None:
+def dbg_lib() -> ctypes.CDLL:
+    """The debug build (profiling switches, ``capr_gemm_test``, ``capr_debug_*`` micro-benchmarks).  Never used for scoring."""
+    global _dbg_lib
+    if _dbg_lib is None:
+        if not DBG_LIB_PATH.exists():
+            raise NativeLibraryMissing(f"{DBG_LIB_PATH} not found: run `make` in the repo root")
+        handle = ctypes.CDLL(str(DBG_LIB_PATH))
+        for name, (restype, argtypes) in {**SIGNATURES, **DEBUG_SIGNATURES}.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _dbg_lib = handle
+    return _dbg_lib
+
+
+def check(rc: int, handle=None) -> None:
     """Map a capr_status to the exception type the reference would raise (SURVEY.md §8b 'Errors')."""
     if rc == CAPR_OK:
         return
-    msg = (lib().capr_last_error() or b"").decode("utf-8", "replace")
+    msg = ((handle or lib()).capr_last_error() or b"").decode("utf-8", "replace")
     if rc in (BAD_SHAPE, UNSUPPORTED):
         raise ValueError(msg)
     raise RuntimeError(f"capr_b200 error {rc}: {msg}")

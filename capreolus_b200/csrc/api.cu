@@ -27,6 +27,31 @@ int sm_count() {
   return n;
 }
 
+int device_of(const void* p) {
+  if (!p) return -1;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
+}
+
+void DeviceGuard::enter(int device) {
+  if (device < 0) return;
+  if (cudaGetDevice(&prev) != cudaSuccess) {
+    cudaGetLastError();
+    prev = -1;
+    return;
+  }
+  if (device != prev && cudaSetDevice(device) == cudaSuccess) switched = true;
+}
+DeviceGuard::DeviceGuard(const void* device_ptr) { enter(device_of(device_ptr)); }
+DeviceGuard::DeviceGuard(int device) { enter(device); }
+DeviceGuard::~DeviceGuard() {
+  if (switched && prev >= 0) cudaSetDevice(prev);
+}
+
 }  // namespace capr
 
 extern "C" {

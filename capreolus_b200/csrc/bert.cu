@@ -338,6 +338,7 @@ struct Model {
   float *pool_w = nullptr, *pool_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
   std::vector<void*> owned;
   int sms = 0;
+  int device = -1;              // the device the weights live on (capr_bert_create); every later call runs there
   bool ffma_attention = false;  // CAPR_BERT_ATTENTION=ffma: force the fp32 CUDA-core attention (A/B tests)
   bool attention_v1 = false;    // CAPR_BERT_ATTENTION=v1: the first tensor-core attention (128 queries per CTA), for A/B tests
   bool attention_v2 = false;    // CAPR_BERT_ATTENTION=v2: one CTA per (sequence, head, 256 queries) instead of the persistent kernel
@@ -494,9 +495,11 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
                "%s: hidden must be a multiple of 64 and <= %d, intermediate a multiple of 64", fn, 32 * LN_MAXPER);
   for (int i = 0; i < n_weights; ++i) CAPR_REQUIRE(weights[i], CAPR_ERR_BAD_POINTER, "%s: weight %d is null", fn, i);
   cudaStream_t st = (cudaStream_t)stream;
+  capr::DeviceGuard device_guard(weights[0]);  // allocate and build the snapshot on the device that owns the weights
   Model* m = new (std::nothrow) Model();
   CAPR_REQUIRE(m, CAPR_ERR_CUDA, "%s: out of host memory", fn);
   m->cfg = *cfg;
+  m->device = capr::device_of(weights[0]);
   m->mode = precision_mode == CAPR_BERT_BF16X3 ? 3 : 1;
   m->sms = sm_count();
   {
@@ -576,6 +579,7 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
                     const float* x_in = nullptr) {
   Model* m = (Model*)h;
   CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
+  capr::DeviceGuard device_guard(m->device);
   CAPR_REQUIRE(n_seq >= 0 && L > 0 && n_hidden >= 0, CAPR_ERR_BAD_SHAPE, "%s: n_seq=%d L=%d", fn, n_seq, L);
   if (n_seq == 0) return CAPR_OK;
   CAPR_REQUIRE(x_in || L <= m->cfg.max_pos, CAPR_ERR_BAD_SHAPE, "%s: sequence length %d exceeds max_position_embeddings %d", fn, L, m->cfg.max_pos);
@@ -647,9 +651,14 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A4_SMEM));
   }
+#ifdef CAPR_DEBUG_BUILD
   const char* adbg = getenv("CAPR_ATTN_DEBUG");
   // CAPR_ATTN_TRACE=<device pointer, decimal>: 256 int64 clock stamps of one CTA of attention_tc2_kernel (scripts/attn_trace.py)
   const char* atr = getenv("CAPR_ATTN_TRACE");
+#else
+  const char* adbg = nullptr;
+  const char* atr = nullptr;
+#endif
   const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo, adbg ? atoi(adbg) : 0,
                       atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr};
   const int att_tc2_grid = n_seq * heads * ((L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ));
@@ -748,6 +757,7 @@ int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, in
   const char* fn = "capr_parade_head";
   Model* m = (Model*)agg;
   CAPR_REQUIRE(m, CAPR_ERR_BAD_POINTER, "%s: null handle", fn);
+  capr::DeviceGuard device_guard(m->device);
   CAPR_REQUIRE(B >= 0 && P > 0 && L > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d P=%d L=%d", fn, B, P, L);
   if (B == 0) return CAPR_OK;
   CAPR_REQUIRE(last_hidden && initial_cls && pos_emb && lin_w && lin_b && scores && workspace, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
@@ -774,12 +784,14 @@ int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, in
   return CAPR_OK;
 }
 
+#ifdef CAPR_DEBUG_BUILD
 // Debug / test entry: C = A . W^T + bias through the same tcgen05 kernel (A [M,K], W [N,K], fp32 device buffers).
 int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c, capr_stream_t stream) {
   const char* fn = "capr_gemm_test";
   CAPR_REQUIRE(a && w && bias && c, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0 && pick_bn(N) > 0, CAPR_ERR_BAD_SHAPE, "%s: need K %% 64 == 0 and N %% 32 == 0", fn);
   cudaStream_t st = (cudaStream_t)stream;
+  capr::DeviceGuard device_guard(a);
   Model m;
   m.mode = precision_mode == CAPR_BERT_BF16X3 ? 3 : 1;
   m.sms = sm_count();
@@ -807,5 +819,6 @@ int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int
   if (!rc && e != cudaSuccess) return cuda_fail(e, "capr_gemm_test");
   return rc;
 }
+#endif  // CAPR_DEBUG_BUILD
 
 }  // extern "C"

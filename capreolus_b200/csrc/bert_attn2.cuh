@@ -44,7 +44,11 @@ struct Attn2Args {
 };
 
 // trace layout: 64 slots per role; roles: 0 producer, 1 MMA, 2 softmax block 0 (warp 4), 3 softmax block 1 (warp 8)
+#ifdef CAPR_DEBUG_BUILD
 #define CAPR_TR(role, slot) do { if (a.trace && blockIdx.x == 148 && lane == 0 && (slot) < 64) a.trace[(role) * 64 + (slot)] = clock64(); } while (0)
+#else
+#define CAPR_TR(role, slot) do { } while (0)
+#endif
 
 // (hi, lo) bf16 split of two values at once; returns the packed words {lo16 = a, hi16 = b}
 __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hw, uint32_t& lw) {
@@ -138,7 +142,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
         CAPR_TR(0, 1 + t);  // producer: stage free, issuing loads of tile t
         unsigned char* st = sKV + stage * AT_KV_STAGE_BYTES;
         const int row = tok0 + t * AT_BK;
-        if ((a.debug & 4) && t >= A2_KV_STAGES) {
+        if (CAPR_DBG(a.debug & 4) && t >= A2_KV_STAGES) {
           if (tc::elect_one()) tc::mbar_arrive(&kv_full[stage]);
         } else if (tc::elect_one()) {
           tc::mbar_expect_tx(&kv_full[stage], AT_KV_STAGE_BYTES);
@@ -169,7 +173,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * 128 + buf * AT_BK);
         if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < ((a.debug & 8) ? 0 : AT_DH / 16); ++k) {
+          for (int k = 0; k < (CAPR_DBG(a.debug & 8) ? 0 : AT_DH / 16); ++k) {
             const uint32_t ko = k * 32;
             tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, k != 0);
             tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
@@ -189,7 +193,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
         const uint32_t d_tmem = tmem_base + (uint32_t)(256 + g * AT_DH);
         if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < ((a.debug & 2) ? 0 : AT_BK / 16); ++k) {
+          for (int k = 0; k < (CAPR_DBG(a.debug & 2) ? 0 : AT_BK / 16); ++k) {
             const uint32_t pk = k * 32;        // 16 keys = 32 bytes along P's K-major rows
             const uint32_t vk = k * 16 * 128;  // 16 keys = 16 rows of the V tile
             tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(p_hi + pk), make_sw128_mnmajor_desc(v_hi + vk), idesc_pv, (t | k) != 0);
@@ -238,7 +242,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_empty[g * 2 + buf]);
-      if (a.debug & 1) {
+      if (CAPR_DBG(a.debug & 1)) {
         tc::mbar_wait(&p_empty[g], (uint32_t)((t & 1) ^ 1));
         tc::mbar_arrive(&p_full[g]);
         continue;

@@ -224,6 +224,7 @@ int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidd
                        int H, int maxqlen, const float* mu, const float* sigma, int K, int cls_mode, const float* w1, const float* b1,
                        int combine_hidden, const float* w2, const float* b2, float* feats, float* scores, void* workspace,
                        size_t workspace_bytes, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(mask);  // act on the device that owns the caller's buffers
   const char* fn = "capr_cedrknrm_head";
   CAPR_REQUIRE(B >= 0 && P > 0 && L > 1 && H > 0 && maxqlen > 0 && K > 0 && n_layers >= 0 && combine_hidden >= 0, CAPR_ERR_BAD_SHAPE,
                "%s: bad shape B=%d P=%d L=%d H=%d maxqlen=%d K=%d layers=%d", fn, B, P, L, H, maxqlen, K, n_layers);

@@ -28,6 +28,33 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// Profiling switches (CAPR_DEBUG_FLAGS, CAPR_ATTN_DEBUG, CAPR_PACRR_DEBUG: skip the pooling / the MMAs / the gathers, results
+// invalid) exist only in the debug build of the library (libcapr_b200_dbg.so, -DCAPR_DEBUG_BUILD); in the product library
+// every test of them folds to a compile-time 0.
+#ifdef CAPR_DEBUG_BUILD
+#define CAPR_DBG(expr) (expr)
+#else
+#define CAPR_DBG(expr) 0
+#endif
+
+// The kernels, cudaFuncSetAttribute, sm_count() and the occupancy queries all act on the CURRENT device, while a caller hands
+// the C ABI a stream and pointers that belong to its tensors' device (a model on cuda:1 while cuda:0 is current).  Every entry
+// point that enqueues work therefore makes the device that owns one of its device pointers (or the one stored in its handle)
+// current for the duration of the call and restores the previous one on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* device_ptr);
+  explicit DeviceGuard(int device);
+  ~DeviceGuard();
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+ private:
+  void enter(int device);
+};
+int device_of(const void* device_ptr);  // -1: not a device pointer (or null)
+
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);

@@ -238,6 +238,7 @@ extern "C" {
 int capr_convknrm_proj_cols(int maxngram, int F) { return (maxngram <= 0 || F <= 0) ? 0 : conv_slots(maxngram) * F; }
 
 int capr_convknrm_project(const float* emb, int V, int E, const float* const* conv_w, int maxngram, int F, float* proj, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(emb);  // act on the device that owns the caller's buffers
   const char* fn = "capr_convknrm_project";
   CAPR_REQUIRE(V > 0 && E > 0 && F > 0 && maxngram > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape V=%d E=%d F=%d maxngram=%d", fn, V, E, F, maxngram);
   CAPR_REQUIRE(maxngram <= CONV_MAX_NGRAM, CAPR_ERR_UNSUPPORTED, "%s: maxngram=%d > %d is not supported", fn, maxngram, CONV_MAX_NGRAM);
@@ -265,6 +266,7 @@ int capr_convknrm_forward(const int64_t* query, const int64_t* doc, int B, int Q
                           const float* const* conv_b, int crossmatch, const float* mu, const float* sigma, int K, const float* w1,
                           const float* b1, int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats_out,
                           void* workspace, size_t workspace_bytes, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(proj);  // act on the device that owns the caller's buffers
   const char* fn = "capr_convknrm_forward";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && F > 0 && maxngram > 0 && K > 0 && hidden >= 0, CAPR_ERR_BAD_SHAPE,
                "%s: bad shape B=%d Q=%d D=%d V=%d F=%d maxngram=%d K=%d", fn, B, Q, D, V, F, maxngram, K);

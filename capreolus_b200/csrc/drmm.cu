@@ -329,6 +329,7 @@ extern "C" int capr_drmm_forward(const int64_t* query, const int64_t* doc, const
                                  const float* ffw_b1, int nodes, const float* ffw_w2, const float* ffw_b2,
                                  const float* gate_w, const float* out_w, const float* out_b, float* scores,
                                  float* hist_out, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table);  // act on the device that owns the caller's buffers
   const char* fn = "capr_drmm_forward";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && nodes > 0 && nbins > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d nodes=%d nbins=%d", fn, B, Q, D, V, nodes, nbins);
   CAPR_REQUIRE(pitch > 0 && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: table pitch %d must be a positive multiple of 16", fn, pitch);
@@ -359,6 +360,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
                                     const float* bin_ub, int hist_type, int gate_type, const float* ffw_w1, const float* ffw_b1,
                                     int nodes, const float* ffw_w2, const float* ffw_b2, const float* gate_w, const float* out_w,
                                     const float* out_b, float* scores, float* hist_out, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table_hi);  // act on the device that owns the caller's buffers
   const char* fn = "capr_drmm_forward_tc";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && nodes > 0 && nbins > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d nodes=%d nbins=%d", fn, B, Q, D, V, E, nodes, nbins);
   CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 16 and >= E (capr_table_pitch_bf16)", fn, pitch);

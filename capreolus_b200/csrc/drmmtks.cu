@@ -154,6 +154,7 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
                                        const void* table_lo, int V, int E, int pitch, int topk, const float* ffw_w, const float* ffw_b,
                                        const float* gate_w, const float* out_w, const float* out_b, float* scores, float* topk_out,
                                        capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table_hi);  // act on the device that owns the caller's buffers
   const char* fn = "capr_drmmtks_forward_tc";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && topk > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d topk=%d", fn, B, Q, D, V, E, topk);
   CAPR_REQUIRE(topk <= D, CAPR_ERR_BAD_SHAPE, "%s: topk=%d is out of range for maxdoclen=%d (torch.topk raises in the reference)", fn, topk, D);

@@ -202,6 +202,7 @@ extern "C" {
 
 int capr_simmat_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
                         int pitch, float* sim, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table);  // act on the device that owns the caller's buffers
   int rc = check_common("capr_simmat_forward", query, doc, B, Q, D, table, V, pitch);
   if (rc) return rc;
   CAPR_REQUIRE(sim, CAPR_ERR_BAD_POINTER, "capr_simmat_forward: null output");
@@ -219,6 +220,7 @@ int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, in
                       int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1,
                       int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
                       float* stats, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table);  // act on the device that owns the caller's buffers
   int rc = check_common("capr_knrm_forward", query, doc, B, Q, D, table, V, pitch);
   if (rc) return rc;
   CAPR_REQUIRE(K > 0 && hidden >= 0, CAPR_ERR_BAD_SHAPE, "capr_knrm_forward: K=%d hidden=%d", K, hidden);

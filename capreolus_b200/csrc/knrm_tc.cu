@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
         ub = unit & 1;
         ps.wait_full(s, ub);
         const int nvalid = min(NT_DOCS, a.pr.D - h * NT_DOCS) - pw * SLICE;  // columns of this slice that exist
-        if (!(a.flags & CAPR_DEBUG_SKIP_POOL) && nvalid > 0) {
+        if (!CAPR_DBG(a.flags & 0x100 /*CAPR_DEBUG_SKIP_POOL*/) && nvalid > 0) {
           const float4* row = reinterpret_cast<const float4*>(half_tile(s, ub) + lane * HALF_PITCH + pw * SLICE);
 #pragma unroll 2
           for (int g = 0; g < SLICE / 4; ++g) {
@@ -179,6 +179,7 @@ extern "C" {
 int capr_table_pitch_bf16(int E) { return E <= 0 ? 0 : ((E + 15) / 16) * 16; }
 
 int capr_table_prepare_bf16(const float* emb, int V, int E, void* hi, void* lo, int pitch, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(emb);  // act on the device that owns the caller's buffers
   CAPR_REQUIRE(V > 0 && E > 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare_bf16: V=%d E=%d must be positive", V, E);
   CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare_bf16: pitch=%d must be a multiple of 16 and >= E=%d", pitch, E);
   CAPR_REQUIRE(emb && hi && lo, CAPR_ERR_BAD_POINTER, "capr_table_prepare_bf16: null pointer");
@@ -191,6 +192,7 @@ int capr_table_prepare_bf16(const float* emb, int V, int E, void* hi, void* lo, 
 int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q, int D, const void* table_hi, const void* table_lo, int V,
                          int E, int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1, int hidden,
                          const float* w2, const float* b2, int flags, float* scores, float* feats, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table_hi);  // act on the device that owns the caller's buffers
   const char* fn = "capr_knrm_forward_tc";
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0 && E > 0 && K > 0 && hidden >= 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d E=%d K=%d", fn, B, Q, D, V, E, K);
   CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "%s: pitch=%d must be a multiple of 16 and >= E (capr_table_pitch_bf16)", fn, pitch);

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) pair_hinge_kernel(const float* __restrict
 
 extern "C" int capr_pair_hinge(const float* pos, const float* neg, int B, float* loss, float* grad_pos, float* grad_neg,
                                capr_stream_t stream) {
+  capr::DeviceGuard device_guard(pos);  // act on the device that owns the caller's buffers
   CAPR_REQUIRE(B > 0, CAPR_ERR_BAD_SHAPE, "capr_pair_hinge: B=%d must be positive", B);
   CAPR_REQUIRE(pos && neg && loss, CAPR_ERR_BAD_POINTER, "capr_pair_hinge: null pointer");
   capr::pair_hinge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pos, neg, B, loss, grad_pos, grad_neg);

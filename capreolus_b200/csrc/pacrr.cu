@@ -10,6 +10,8 @@
 // relu(max_f x_f) == max_f relu(x_f), so ReLU is applied once after the filter max.  Each lane keeps a
 // running top-k of its columns; lanes are merged with k rounds of warp max.  The reference's [B,F,Q,D]
 // conv output (2 MB per pair and n-gram) never exists.
+#include <mutex>
+
 #include "simtc.cuh"
 
 namespace capr {
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc3_kernel(const Pacr
     const int NB = a.Q * NBJ;
     uint32_t acc_phase = 0, conv_phase = 0;  // one bit per buffer
     int unit = 0;
-    const int dbg = a.pr.debug;  // profiling only (CAPR_PACRR_DEBUG): 0x10000 no build, 0x20000 no MMA, 0x40000 no reduce, 0x80000 no fence
+    const int dbg = CAPR_DBG(a.pr.debug);  // profiling only (CAPR_PACRR_DEBUG): 0x10000 no build, 0x20000 no MMA, 0x40000 no reduce, 0x80000 no fence
     for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x, unit += halves_of(a.pr)) {
       drain_pair(s, a.pr, tmem_base, pair, unit, acc_phase, tid);  // -> s.sim (fp32, zero halo); ends with epi_barrier
       float top[3][KM];
@@ -511,6 +513,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
                      const float* const* conv_w, const float* const* conv_b, const float* l1w, const float* l1b, const float* l2w,
                      const float* l2b, const float* l3w, const float* l3b, int combine, int nonlin, float* scores, float* topk_out,
                      capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table);  // act on the device that owns the caller's buffers
   CAPR_REQUIRE(B >= 0 && Q > 0 && D > 0 && V > 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape B=%d Q=%d D=%d V=%d", fn, B, Q, D, V);
   CAPR_REQUIRE(mingram >= 1 && maxgram >= mingram && nfilters > 0 && kmax > 0 && combine > 0, CAPR_ERR_BAD_SHAPE, "%s: bad config mingram=%d maxgram=%d nfilters=%d kmax=%d combine=%d", fn, mingram, maxgram, nfilters, kmax, combine);
   CAPR_REQUIRE(nonlin >= 0 && nonlin <= 2, CAPR_ERR_BAD_SHAPE, "%s: nonlinearity must be none, relu or tanh", fn);
@@ -531,8 +534,17 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = tc_engine ? nullptr : (const float*)table;
   if (tc_engine) a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E, 0};
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
-  // Stage the filter taps in constant memory (stream-ordered device-to-device copies; the constant bank
-  // is per device, so concurrent PACRR calls with different weights must share one stream).
+  // Stage the filter taps in constant memory (stream-ordered device-to-device copies).  The constant bank is one per device, so
+  // calls are serialised per device: a call on another stream (or thread) first waits for the event recorded behind the previous
+  // call's kernel before it overwrites the taps, and the host-side section between the copies and the launch holds a mutex.
+  static std::mutex conv_bank_mutex;
+  static cudaEvent_t conv_bank_free[64] = {};
+  std::lock_guard<std::mutex> conv_bank_lock(conv_bank_mutex);
+  int cur_dev = 0;
+  CAPR_CHECK_CUDA(cudaGetDevice(&cur_dev));
+  CAPR_REQUIRE(cur_dev >= 0 && cur_dev < 64, CAPR_ERR_UNSUPPORTED, "%s: device index %d out of range", fn, cur_dev);
+  if (conv_bank_free[cur_dev]) CAPR_CHECK_CUDA(cudaStreamWaitEvent(st, conv_bank_free[cur_dev], 0));
+  else CAPR_CHECK_CUDA(cudaEventCreateWithFlags(&conv_bank_free[cur_dev], cudaEventDisableTiming));
   for (int g = 0; g <= maxgram - mingram; ++g) {
     const int n = mingram + g;
     CAPR_REQUIRE(conv_w[g] && conv_b[g], CAPR_ERR_BAD_POINTER, "%s: null conv weight %d", fn, g);
@@ -557,7 +569,9 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
     CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: shared memory budget exceeded", fn);
     CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit row offsets", fn);
     a.pr.single = 1;
+#ifdef CAPR_DEBUG_BUILD
     if (const char* de = getenv("CAPR_PACRR_DEBUG")) a.pr.debug = (int)strtol(de, nullptr, 0) & 0x1FF0000;
+#endif
     if (kmax <= 2) {
       CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       pacrr_tc3_kernel<2><<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
@@ -577,6 +591,7 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
     pacrr_kernel<<<B < sms ? B : sms, NT, smem, st>>>(a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
+  CAPR_CHECK_CUDA(cudaEventRecord(conv_bank_free[cur_dev], st));
   return CAPR_OK;
 }
 

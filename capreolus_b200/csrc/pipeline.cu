@@ -153,6 +153,16 @@ rank_by_query_kernel(const float* __restrict__ scores, const long long* __restri
   }
 }
 
+// ---- narrow token ids -> the int64 rows the scoring kernels take --------------------------------------------------------
+// The reference extractor emits np.long ids (embedtext.py:146-147): 8 bytes per token, 4 352 B per (|q|=32, |d|=512) pair,
+// which is what bounds the host -> device leg of the predict loop (448 MB per 100 k pairs).  A 30 k-word vocabulary (and its
+// negative OOV ids) fits int16, so the host side may ship ids as int16 / int32 and widen them here: 2 + 8 bytes of HBM
+// traffic per token, sign-extending (OOV ids stay negative, 0 stays <pad>).
+template <typename T>
+__global__ void __launch_bounds__(256) widen_ids_kernel(const T* __restrict__ src, size_t n, long long* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (long long)src[i];
+}
+
 }  // namespace capr
 
 using namespace capr;
@@ -162,6 +172,7 @@ extern "C" {
 int capr_assemble_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off, int n_docs,
                         const float* idf_store, const int32_t* qidx, const int32_t* didx, int N, int Q, int D, int64_t* query_out,
                         int64_t* doc_out, float* idf_out, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(q_store);  // act on the device that owns the caller's buffers
   const char* fn = "capr_assemble_pairs";
   CAPR_REQUIRE(N >= 0 && Q > 0 && D > 0 && n_queries >= 0 && n_docs >= 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape N=%d Q=%d D=%d", fn, N, Q, D);
   if (N == 0) return CAPR_OK;
@@ -180,6 +191,7 @@ int capr_assemble_pairs(const int32_t* q_store, const int64_t* q_off, int n_quer
 int capr_assemble_bert_pairs(const int32_t* q_store, const int64_t* q_off, int n_queries, const int32_t* d_store, const int64_t* d_off,
                              int n_docs, const int32_t* qidx, const int32_t* didx, int N, int P, int L, int maxqlen, int padq, int passagelen,
                              int stride, int cls_id, int sep_id, int pad_id, int64_t* ids, int64_t* mask, int64_t* seg, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(q_store);  // act on the device that owns the caller's buffers
   const char* fn = "capr_assemble_bert_pairs";
   CAPR_REQUIRE(N >= 0 && P > 0 && L > 3 && maxqlen >= 0 && passagelen > 0 && stride > 0 && n_queries >= 0 && n_docs >= 0, CAPR_ERR_BAD_SHAPE,
                "%s: bad shape N=%d P=%d L=%d maxqlen=%d passagelen=%d stride=%d", fn, N, P, L, maxqlen, passagelen, stride);
@@ -199,6 +211,7 @@ int capr_assemble_bert_pairs(const int32_t* q_store, const int64_t* q_off, int n
 
 int capr_rank_by_query(const float* scores, const int64_t* seg_off, int n_queries, int max_segment, float* rounded, int32_t* order,
                        capr_stream_t stream) {
+  capr::DeviceGuard device_guard(scores);  // act on the device that owns the caller's buffers
   const char* fn = "capr_rank_by_query";
   CAPR_REQUIRE(n_queries >= 0 && max_segment >= 0, CAPR_ERR_BAD_SHAPE, "%s: bad shape n_queries=%d max_segment=%d", fn, n_queries, max_segment);
   if (n_queries == 0 || max_segment == 0) return CAPR_OK;
@@ -212,6 +225,23 @@ int capr_rank_by_query(const float* scores, const int64_t* seg_off, int n_querie
   if (max_segment <= 128) rank_by_query_kernel<128><<<grid, 64, 0, st>>>(scores, so, n_queries, rounded, order);
   else if (max_segment <= 1024) rank_by_query_kernel<1024><<<grid, 512, 0, st>>>(scores, so, n_queries, rounded, order);
   else rank_by_query_kernel<4096><<<grid, 1024, 0, st>>>(scores, so, n_queries, rounded, order);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+int capr_widen_ids(const void* src, int src_bytes, size_t n, int64_t* dst, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(dst);  // act on the device that owns the caller's buffers
+  const char* fn = "capr_widen_ids";
+  CAPR_REQUIRE(src_bytes == 2 || src_bytes == 4, CAPR_ERR_BAD_SHAPE, "%s: src_bytes=%d must be 2 (int16) or 4 (int32)", fn, src_bytes);
+  if (n == 0) return CAPR_OK;
+  CAPR_REQUIRE(src && dst, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(((uintptr_t)src & (uintptr_t)(src_bytes - 1)) == 0 && ((uintptr_t)dst & 7) == 0, CAPR_ERR_BAD_POINTER, "%s: misaligned pointer", fn);
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  const size_t want = (n + 255) / 256;
+  const int grid = (int)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
+  if (src_bytes == 2) widen_ids_kernel<short><<<grid, 256, 0, (cudaStream_t)stream>>>((const short*)src, n, (long long*)dst);
+  else widen_ids_kernel<int><<<grid, 256, 0, (cudaStream_t)stream>>>((const int*)src, n, (long long*)dst);
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;
 }

@@ -248,7 +248,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
           tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
           const uint32_t base = tc::smem_u32(s.dbuf(d_stage));
-          if ((a + 1 < atoms || sub < last_chunks) && !(pr.debug & 0x800)) {  // tail chunks of a partial last atom are never read
+          if ((a + 1 < atoms || sub < last_chunks) && !CAPR_DBG(pr.debug & 0x800)) {  // tail chunks of a partial last atom are never read
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int r = rsub + 16 * j;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int halves = halves_of(pr);
   const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, 128, NT_DOCS);
-  const bool skip = (pr.debug & 0x400) != 0;
+  const bool skip = CAPR_DBG(pr.debug & 0x400) != 0;
   uint32_t q_phase = 0, acc_phase = 0, d_phase = 0;  // q/acc: one bit per buffer
   int d_stage = 0, it = 0, unit = 0;
   const int nst = ring_depth(pr);
@@ -402,7 +402,7 @@ __device__ __forceinline__ void drain_loop(const Smem& s, const Problem& pr, uin
   const int col_half = warp >> 2;
   const int dtid = (warp >> 2) * 64 + (warp & 1) * 32 + lane;  // 0..127 over the four drain warps
   const uint32_t lane_off = (uint32_t)((warp & 1) * 32) << 16;
-  const bool skip_stores = (pr.debug & CAPR_DEBUG_SKIP_DRAIN) != 0;
+  const bool skip_stores = CAPR_DBG(pr.debug & 0x200 /*CAPR_DEBUG_SKIP_DRAIN*/) != 0;
   uint32_t full_phase = 0, empty_phase = 0;  // one bit per buffer
   int unit = 0, it = 0;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {

@@ -34,6 +34,7 @@ extern "C" {
 int capr_table_pitch(int E) { return E <= 0 ? 0 : ((E + 15) / 16) * 16; }
 
 int capr_table_prepare(const float* emb, int V, int E, float* table, int pitch, capr_stream_t stream) {
+  capr::DeviceGuard device_guard(emb);  // act on the device that owns the caller's buffers
   CAPR_REQUIRE(V > 0 && E > 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare: V=%d E=%d must be positive", V, E);
   CAPR_REQUIRE(pitch >= E && pitch % 16 == 0, CAPR_ERR_BAD_SHAPE, "capr_table_prepare: pitch=%d must be a multiple of 16 and >= E=%d", pitch, E);
   CAPR_REQUIRE(emb && table, CAPR_ERR_BAD_POINTER, "capr_table_prepare: null pointer");

@@ -10,11 +10,38 @@ from __future__ import annotations
 import torch
 
 
-class PinnedBatch:
-    """A host batch (dict of tensors / lists as the DataLoader collates them) moved to pinned memory once."""
+def _narrowest(t: torch.Tensor) -> torch.dtype:
+    """The narrowest signed integer dtype that holds every value of an int64 tensor (ids: 0 = <pad>, < 0 = OOV keep their sign)."""
+    if t.numel() == 0:
+        return torch.int16
+    lo, hi = int(t.min()), int(t.max())
+    if -32768 <= lo and hi <= 32767:
+        return torch.int16
+    if -(2 ** 31) <= lo and hi <= 2 ** 31 - 1:
+        return torch.int32
+    return torch.int64
 
-    def __init__(self, batch: dict):
-        self.tensors = {k: (v.contiguous().pin_memory() if not v.is_pinned() else v) for k, v in batch.items() if torch.is_tensor(v)}
+
+class PinnedBatch:
+    """A host batch (dict of tensors / lists as the DataLoader collates them) moved to pinned memory once.
+
+    ``narrow_ids=True`` (default) stores int64 tensors (token ids, BERT masks / segment ids) in the narrowest of int16 / int32 /
+    int64 that holds their values -- the reference extractor emits ``np.long`` (``embedtext.py:146-147``), 4 352 B per
+    (|q|=32, |d|=512) pair, which bounds the host -> device leg of the predict loop; a 30 k vocabulary fits int16 (1 088 B).
+    ``PipelinedPredictor`` widens them on the device (``capr_widen_ids``), so the rerankers still see int64.  ``wide`` names
+    the tensors that were narrowed."""
+
+    def __init__(self, batch: dict, narrow_ids: bool = True):
+        self.tensors, self.wide = {}, {}
+        for k, v in batch.items():
+            if not torch.is_tensor(v):
+                continue
+            if narrow_ids and v.dtype == torch.int64:
+                dt = _narrowest(v)
+                if dt != torch.int64:
+                    self.wide[k] = torch.int64
+                    v = v.to(dt)
+            self.tensors[k] = v if v.is_pinned() else v.contiguous().pin_memory()
         self.n = len(next(iter(self.tensors.values())))
         self.bytes_per_item = sum(v[0].numel() * v.element_size() for v in self.tensors.values()) if self.n else 0
 
@@ -34,14 +61,15 @@ class PipelinedPredictor:
         self._out_host = None
 
     def _buffers(self, pb: PinnedBatch):
-        sig = tuple((k, v.dtype, tuple(v.shape[1:])) for k, v in pb.tensors.items())
+        sig = tuple((k, v.dtype, tuple(v.shape[1:]), k in pb.wide) for k, v in pb.tensors.items())
         if self._bufs is None or self._bufs[0] != sig:
-            bufs = [{k: torch.empty((self.chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for k, v in pb.tensors.items()}
-                    for _ in range(2)]
-            self._bufs = (sig, bufs)
+            mk = lambda v, dt: torch.empty((self.chunk,) + tuple(v.shape[1:]), dtype=dt, device=self.device)
+            staged = [{k: mk(v, v.dtype) for k, v in pb.tensors.items()} for _ in range(2)]
+            wide = [{k: mk(pb.tensors[k], dt) for k, dt in pb.wide.items()} for _ in range(2)]  # int64 rows the rerankers consume
+            self._bufs = (sig, staged, wide)
         if self._out_host is None or self._out_host.shape[0] < pb.n:
             self._out_host = torch.empty(pb.n, dtype=torch.float32).pin_memory()
-        return self._bufs[1]
+        return self._bufs[1], self._bufs[2]
 
     def schedule(self, n: int) -> list:
         """``[(lo, hi), ...]`` covering ``range(n)``: ramp-up chunks first (if enabled), then full chunks."""
@@ -57,27 +85,39 @@ class PipelinedPredictor:
 
     @torch.no_grad()
     def predict(self, pb: PinnedBatch) -> torch.Tensor:
-        """Scores for every item of ``pb`` as a pinned host fp32 tensor ``[n]`` (valid after this call returns)."""
-        bufs = self._buffers(pb)
-        main = torch.cuda.current_stream(self.device)
-        spans = self.schedule(pb.n)
-        copied = [torch.cuda.Event() for _ in spans]
-        scored = [torch.cuda.Event() for _ in spans]
-        self.copy_stream.wait_stream(main)
-        for i, (lo, hi) in enumerate(spans):
-            buf = bufs[i % 2]
-            with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(scored[i - 2])  # buffer reuse
-                for k, v in pb.tensors.items():
-                    buf[k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
-                copied[i].record(self.copy_stream)
-            main.wait_event(copied[i])
-            scores = self.reranker.test({k: v[: hi - lo] for k, v in buf.items()})
-            self._out_host[lo:hi].copy_(scores.view(-1), non_blocking=True)
-            scored[i].record(main)
-        main.synchronize()
-        return self._out_host[: pb.n]
+        """Scores for every item of ``pb`` as a host fp32 tensor ``[n]`` (a fresh tensor: a later call does not overwrite it)."""
+        from capreolus_b200 import _lib
+
+        with torch.cuda.device(self.device):
+            staged, wide = self._buffers(pb)
+            main = torch.cuda.current_stream(self.device)
+            spans = self.schedule(pb.n)
+            copied = [torch.cuda.Event() for _ in spans]
+            scored = [torch.cuda.Event() for _ in spans]
+            self.copy_stream.wait_stream(main)
+            for i, (lo, hi) in enumerate(spans):
+                buf, wbuf = staged[i % 2], wide[i % 2]
+                with torch.cuda.stream(self.copy_stream):
+                    if i >= 2:
+                        self.copy_stream.wait_event(scored[i - 2])  # buffer reuse
+                    for k, v in pb.tensors.items():
+                        buf[k][: hi - lo].copy_(v[lo:hi], non_blocking=True)
+                    copied[i].record(self.copy_stream)
+                main.wait_event(copied[i])
+                view = {}
+                for k, v in buf.items():
+                    if k in wbuf:  # narrow ids -> int64 on the device (2 + 8 bytes of HBM traffic per token)
+                        src, dst = v[: hi - lo], wbuf[k][: hi - lo]
+                        _lib.check(_lib.lib().capr_widen_ids(src.data_ptr(), src.element_size(), src.numel(), dst.data_ptr(),
+                                                            main.cuda_stream))
+                        view[k] = dst
+                    else:
+                        view[k] = v[: hi - lo]
+                scores = self.reranker.test(view)
+                self._out_host[lo:hi].copy_(scores.view(-1), non_blocking=True)
+                scored[i].record(main)
+            main.synchronize()
+        return self._out_host[: pb.n].clone()
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -70,11 +70,14 @@ int capr_simmat_forward(const int64_t* query, const int64_t* doc, int B, int Q, 
  *   stats  [B,2,K]   (nullable)        backward statistics for d/dmu, d/dsigma
  */
 #define CAPR_KNRM_SCORETANH 1
-/* profiling aids for capr_knrm_forward_tc only (results are NOT valid when set): skip the pooling loop / the TMEM drain */
+#ifdef CAPR_DEBUG_BUILD
+/* profiling aids of the DEBUG build (libcapr_b200_dbg.so) for capr_knrm_forward_tc only; results are NOT valid when set: skip
+ * the pooling loop / the TMEM drain / the MMAs / the gathers.  The product library ignores these bits. */
 #define CAPR_DEBUG_SKIP_POOL 0x100
 #define CAPR_DEBUG_SKIP_DRAIN 0x200
 #define CAPR_DEBUG_SKIP_MMA 0x400
 #define CAPR_DEBUG_SKIP_GATHER 0x800
+#endif
 int capr_knrm_forward(const int64_t* query, const int64_t* doc, int B, int Q, int D, const float* table, int V,
                       int pitch, const float* mu, const float* sigma, int K, const float* w1, const float* b1,
                       int hidden, const float* w2, const float* b2, int flags, float* scores, float* feats,
@@ -190,6 +193,11 @@ int capr_assemble_bert_pairs(const int32_t* q_store, const int64_t* q_off, int n
                              int n_docs, const int32_t* qidx, const int32_t* didx, int N, int P, int L, int maxqlen, int padq,
                              int passagelen, int stride, int cls_id, int sep_id, int pad_id, int64_t* ids, int64_t* mask, int64_t* seg,
                              capr_stream_t stream);
+/* capr_widen_ids: the host side of the predict loop may ship token ids narrower than the reference's int64
+ * (capreolus/extractor/embedtext.py:146-147 emits np.long; a 30 k vocabulary and its negative OOV ids fit int16): src is
+ * n int16 (src_bytes 2) or int32 (src_bytes 4) ids, dst the sign-extended int64 ids every scoring entry point takes.  Cuts the
+ * host -> device bytes of capreolus/trainer/pytorch.py:342 (`v.to(device)`) 4x / 2x. */
+int capr_widen_ids(const void* src, int src_bytes, size_t n, int64_t* dst, capr_stream_t stream);
 /* capr_rank_by_query replaces the float16 rounding of PytorchTrainer.predict (capreolus/trainer/pytorch.py:345-348) and the
  * per-query sort of Searcher.write_trec_run (capreolus/searcher/__init__.py:48-58).  Pairs of one query are contiguous:
  * seg_off [n_queries+1] int64.  rounded [N] (nullable) = float(float16(score)); order [N]: for query q, order[seg_off[q]+r]
@@ -274,6 +282,9 @@ int capr_cedrknrm_head(const float* hidden, int n_layers, const float* last_hidd
                        int P, int L, int H, int maxqlen, const float* mu, const float* sigma, int K, int cls_mode, const float* w1,
                        const float* b1, int combine_hidden, const float* w2, const float* b2, float* feats, float* scores,
                        void* workspace, size_t workspace_bytes, capr_stream_t stream);
+/* ---- debug build only (libcapr_b200_dbg.so = the same sources with -DCAPR_DEBUG_BUILD + the micro-benchmarks) --------------
+ * None of the following is exported by the product library libcapr_b200.so. */
+#ifdef CAPR_DEBUG_BUILD
 /* Test hook: C[M,N] = A[M,K] . W[N,K]^T + bias through the encoder's tcgen05 GEMM kernel (synchronises the stream). */
 int capr_gemm_test(const float* a, const float* w, const float* bias, int M, int N, int K, int precision_mode, float* c,
                    capr_stream_t stream);
@@ -285,6 +296,7 @@ int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps, int grid,
  * scalar operand from the constant bank (mode 0, the form PACRR's conv uses), from vector registers (mode 1), or as plain FFMA
  * pairs (mode 2).  scratch: >= 64 + grid*256 floats. */
 int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long long* cycles, capr_stream_t stream);
+#endif /* CAPR_DEBUG_BUILD */
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 import sys, torch
 sys.path.insert(0, ".")
 from capreolus_b200 import _lib
-lib = _lib.lib()
+lib = _lib.dbg_lib()
 grid, iters = 148, 2000
 scratch = torch.zeros(64 + grid * 256, device="cuda")
 cyc = torch.zeros(grid, dtype=torch.int64, device="cuda")

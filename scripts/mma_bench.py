@@ -1,7 +1,7 @@
 import torch, sys
 sys.path.insert(0, ".")
 from capreolus_b200 import _lib
-lib = _lib.lib()
+lib = _lib.dbg_lib()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 print("M    N  n_mma n_acc grid  cycles/MMA")
 for grid in (1, 148):

@@ -25,7 +25,8 @@ def test_tcgen05_gemm_matches_fp64_matmul(M, N, K, mode, tol):
     want = (a.double() @ w.double().T + bias.double()).numpy()
     ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
     c = torch.full((M, N), float("nan"), device=DEV)
-    _lib.check(_lib.lib().capr_gemm_test(ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), M, N, K, mode, c.data_ptr(), None))
+    dbg = _lib.dbg_lib()  # the GEMM test hook lives in the debug build only
+    _lib.check(dbg.capr_gemm_test(ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), M, N, K, mode, c.data_ptr(), None), dbg)
     got = c.cpu().numpy()
     assert np.isfinite(got).all()
     err = np.abs(got - want).max() / np.abs(want).max()

@@ -21,14 +21,33 @@ class Extractor:
         self.config = {"maxqlen": Q, "maxdoclen": D}
 
 
-def test_library_exports_every_symbol_the_header_declares():
+def _declared_symbols():
+    """(product, debug-only) symbol sets of include/capr_b200.h: debug-only = declared inside `#ifdef CAPR_DEBUG_BUILD`."""
     header = (ROOT / "include" / "capr_b200.h").read_text()
-    declared = set(re.findall(r"\b(capr_[a-z0-9_]+)\s*\(", header))
+    product, debug, in_dbg = set(), set(), False
+    for line in header.splitlines():
+        if line.startswith("#ifdef CAPR_DEBUG_BUILD"):
+            in_dbg = True
+        elif in_dbg and line.startswith("#endif"):
+            in_dbg = False
+        for name in re.findall(r"\b(capr_[a-z0-9_]+)\s*\(", line):
+            (debug if in_dbg else product).add(name)
+    return product, debug
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    declared, debug_only = _declared_symbols()
     assert declared, "no declarations parsed"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert debug_only == set(_lib.DEBUG_SIGNATURES), debug_only ^ set(_lib.DEBUG_SIGNATURES)
     lib = _lib.lib()  # raises if the .so is missing or lacks a symbol
     for name in declared:
         assert hasattr(lib, name)
+    for name in debug_only:  # micro-benchmarks / test hooks / profiling switches stay out of the product library
+        assert not hasattr(lib, name), f"{name} must not be exported by the product library"
+    dbg = _lib.dbg_lib()
+    for name in declared | debug_only:
+        assert hasattr(dbg, name)
     assert lib.capr_abi_version() == 1
     assert lib.capr_table_pitch(300) == 304 and lib.capr_table_pitch(16) == 16 and lib.capr_table_pitch(1) == 16
 
