@@ -73,6 +73,7 @@ SIGNATURES = {
     "capr_widen_ids": (c_int, [c_void_p, c_int, c_size_t, _i64p, c_void_p]),
     "capr_rank_by_query": (c_int, [_f32p, c_void_p, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_pair_hinge": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
+    "capr_pair_softmax": (c_int, [_f32p, _f32p, c_int, _f32p, _f32p, _f32p, c_void_p]),
     "capr_bert_num_weights": (c_int, [POINTER(BertConfigStruct)]),
     "capr_bert_create": (c_int, [POINTER(BertConfigStruct), POINTER(c_void_p), c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "capr_bert_destroy": (None, [c_void_p]),

@@ -273,6 +273,19 @@ static int launch_attention(int grid, const float* qkv, const long long* mask, i
   return CAPR_OK;
 }
 
+// [CLS] rows (token 0 of every sequence) of the attention context planes and of the fp32 residual stream -> compact [n_seq, H]
+// buffers: the input of the CLS-only tail of the last encoder layer.
+__global__ void __launch_bounds__(256) gather_cls_kernel(const __nv_bfloat16* __restrict__ ctx_hi, const __nv_bfloat16* __restrict__ ctx_lo,
+                                                         const float* __restrict__ x, int L, int H, __nv_bfloat16* __restrict__ c_hi,
+                                                         __nv_bfloat16* __restrict__ c_lo, float* __restrict__ cx) {
+  const size_t src = (size_t)blockIdx.x * L * H, dst = (size_t)blockIdx.x * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    c_hi[dst + i] = ctx_hi[src + i];
+    c_lo[dst + i] = ctx_lo[src + i];
+    cx[dst + i] = x[src + i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pooler + classifier on the [CLS] row of every sequence: logits[n, :] = Wc tanh(Wp x[n*L] + bp) + bc
 // ---------------------------------------------------------------------------------------------------------------
@@ -399,7 +412,7 @@ static int pair_capacity(int sms) {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(sms & ~1), 1, 1);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.blockDim = dim3(G2_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Gemm2Smem<MODE>::BYTES;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -422,7 +435,7 @@ static int launch_gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMa
     if (cap > 0) {
       const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (lin.N / G2_BN);
       const int pairs = pair_tiles < cap ? pair_tiles : cap;
-      gemm2_kernel<MODE><<<2 * pairs, GEMM_THREADS, Gemm2Smem<MODE>::BYTES, st>>>(a_hi, a_lo, lin.pair_hi, lin.pair_lo, g);
+      gemm2_kernel<MODE><<<2 * pairs, G2_THREADS, Gemm2Smem<MODE>::BYTES, st>>>(a_hi, a_lo, lin.pair_hi, lin.pair_lo, g);
       CAPR_CHECK_CUDA(cudaGetLastError());
       return CAPR_OK;
     }
@@ -444,10 +457,14 @@ static int gemm(const Model* m, const CUtensorMap& a_hi, const CUtensorMap& a_lo
 struct Workspace {
   float *x, *y, *qkv;  // qkv: fp32 [Tp,3H] (FFMA attention) or, aliased, two bf16 planes [Tp,3H] (tensor-core attention)
   __nv_bfloat16 *x_hi, *x_lo, *ctx_hi, *ctx_lo, *ffn_hi, *ffn_lo;
+  // compact [Np, .] copies of the [CLS] rows (Np = n_seq rounded up to 128) for the CLS-only tail of the last layer
+  float *cx, *cy;
+  __nv_bfloat16 *cx_hi, *cx_lo, *cctx_hi, *cctx_lo, *cffn_hi, *cffn_lo;
 };
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-static size_t carve(const capr_bert_config& c, size_t T, unsigned char* base, Workspace* w) {
+static size_t carve(const capr_bert_config& c, size_t T, size_t n_seq, unsigned char* base, Workspace* w) {
   const size_t Tp = (T + BM - 1) / BM * BM;
+  const size_t Np = (n_seq + BM - 1) / BM * BM;
   const size_t H = c.hidden, I = c.intermediate;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -464,7 +481,15 @@ static size_t carve(const capr_bert_config& c, size_t T, unsigned char* base, Wo
   __nv_bfloat16* ctx_lo = (__nv_bfloat16*)take(Tp * H * 2);
   __nv_bfloat16* ffn_hi = (__nv_bfloat16*)take(Tp * I * 2);
   __nv_bfloat16* ffn_lo = (__nv_bfloat16*)take(Tp * I * 2);
-  if (w) *w = Workspace{x, y, qkv, x_hi, x_lo, ctx_hi, ctx_lo, ffn_hi, ffn_lo};
+  float* cx = (float*)take(Np * H * 4);
+  float* cy = (float*)take(Np * H * 4);
+  __nv_bfloat16* cx_hi = (__nv_bfloat16*)take(Np * H * 2);
+  __nv_bfloat16* cx_lo = (__nv_bfloat16*)take(Np * H * 2);
+  __nv_bfloat16* cctx_hi = (__nv_bfloat16*)take(Np * H * 2);
+  __nv_bfloat16* cctx_lo = (__nv_bfloat16*)take(Np * H * 2);
+  __nv_bfloat16* cffn_hi = (__nv_bfloat16*)take(Np * I * 2);
+  __nv_bfloat16* cffn_lo = (__nv_bfloat16*)take(Np * I * 2);
+  if (w) *w = Workspace{x, y, qkv, x_hi, x_lo, ctx_hi, ctx_lo, ffn_hi, ffn_lo, cx, cy, cx_hi, cx_lo, cctx_hi, cctx_lo, cffn_hi, cffn_lo};
   return off;
 }
 
@@ -567,7 +592,7 @@ void capr_bert_destroy(capr_bert_t h) {
 size_t capr_bert_workspace_bytes(capr_bert_t h, int n_seq, int L) {
   Model* m = (Model*)h;
   if (!m || n_seq <= 0 || L <= 0) return 0;
-  return carve(m->cfg, (size_t)n_seq * L, nullptr, nullptr);
+  return carve(m->cfg, (size_t)n_seq * L, (size_t)n_seq, nullptr, nullptr);
 }
 
 // Shared body of capr_bert_forward / capr_bert_forward_hidden.  hidden_layers[i] in [0, layers]: 0 = embedding output,
@@ -591,7 +616,7 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
   const size_t T = (size_t)n_seq * L;
   CAPR_REQUIRE(T < (size_t)1 << 31, CAPR_ERR_BAD_SHAPE, "%s: too many tokens in one call (%zu); split the batch", fn, T);
   Workspace ws;
-  const size_t need = carve(m->cfg, T, (unsigned char*)workspace, &ws);
+  const size_t need = carve(m->cfg, T, (size_t)n_seq, (unsigned char*)workspace, &ws);
   CAPR_REQUIRE(workspace_bytes >= need, CAPR_ERR_BAD_SHAPE, "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const int H = m->cfg.hidden, I = m->cfg.intermediate, heads = m->cfg.heads, dh = H / heads;
@@ -660,17 +685,51 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
   const char* atr = nullptr;
 #endif
   const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo, adbg ? atoi(adbg) : 0,
-                      atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr};
+                      atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr, 0};
   const int att_tc2_grid = n_seq * heads * ((L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ));
   const AttnArgs at{L, H, heads, n_seq, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
   const int att_tc_grid = n_seq * heads * ((L + AT_BQ - 1) / AT_BQ);
+  // CLS-only tail: a classification forward consumes row 0 of the last layer only (pooler -> classifier; ptBERTMaxP.py:82,
+  // SURVEY.md App. B "Only row 0 ([CLS]) of the last layer's output is consumed").  The last layer still needs K / V of every
+  // token, but its attention runs for the first query block alone and out-projection, both LayerNorms and the FFN (10 of the 12
+  // weight-matrix units of a layer) run on the n_seq [CLS] rows gathered into compact buffers.  Off when hidden states of the
+  // last layer are requested (CEDR-KNRM, PARADE) or when an A/B attention kernel is selected; CAPR_BERT_CLS_ONLY=0 disables it.
+  const char* cls_env = getenv("CAPR_BERT_CLS_ONLY");
+  const bool cls_only = logits && n_hidden == 0 && tc_attention && !m->attention_v1 && !m->attention_v2 &&
+                        !(cls_env && cls_env[0] == '0');
+  const size_t Np = ((size_t)n_seq + BM - 1) / BM * BM;
+  CUtensorMap cx_hi, cx_lo, cc_hi, cc_lo, cf_hi, cf_lo;
+  if (cls_only) {
+    if ((rc = make_map(&cx_hi, ws.cx_hi, Np, H, BM))) return rc;
+    if ((rc = make_map(&cx_lo, ws.cx_lo, Np, H, BM))) return rc;
+    if ((rc = make_map(&cc_hi, ws.cctx_hi, Np, H, BM))) return rc;
+    if ((rc = make_map(&cc_lo, ws.cctx_lo, Np, H, BM))) return rc;
+    if ((rc = make_map(&cf_hi, ws.cffn_hi, Np, I, BM))) return rc;
+    if ((rc = make_map(&cf_lo, ws.cffn_lo, Np, I, BM))) return rc;
+    if (Np > (size_t)n_seq) {  // pad rows of the compact A operands are read by TMA: keep them finite
+      const size_t pad = Np - (size_t)n_seq, at = (size_t)n_seq;
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cx_hi + at * H, 0, pad * H * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cx_lo + at * H, 0, pad * H * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cctx_hi + at * H, 0, pad * H * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cctx_lo + at * H, 0, pad * H * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cffn_hi + at * I, 0, pad * I * 2, st));
+      CAPR_CHECK_CUDA(cudaMemsetAsync(ws.cffn_lo + at * I, 0, pad * I * 2, st));
+    }
+  }
+  const int cls_row_blocks = (n_seq + 7) / 8;
   for (int l = 0; l < m->cfg.layers; ++l) {
     const Layer& ly = m->layers[l];
+    const bool tail = cls_only && l + 1 == m->cfg.layers;
     if (tc_attention) {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_SPLIT, nullptr, nullptr, qkv_hi, qkv_lo, st))) return rc;
       if (m->attention_v1) attention_tc_kernel<<<att_tc_grid, AT_THREADS, AT_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at);
       else if (m->attention_v2) attention_tc2_kernel<<<att_tc2_grid, A2_THREADS, A2_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
-      else attention_tc4_kernel<<<att_tc2_grid < m->sms ? att_tc2_grid : m->sms, A4_THREADS, A4_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
+      else if (tail) {
+        Attn2Args at_cls = at2;
+        at_cls.q_blocks = 1;  // only block 0 holds the [CLS] query
+        const int items = n_seq * heads;
+        attention_tc4_kernel<<<items < m->sms ? items : m->sms, A4_THREADS, A4_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at_cls);
+      } else attention_tc4_kernel<<<att_tc2_grid < m->sms ? att_tc2_grid : m->sms, A4_THREADS, A4_SMEM, st>>>(q_hi, q_lo, kv_hi, kv_lo, at2);
       CAPR_CHECK_CUDA(cudaGetLastError());
     } else {
       if ((rc = gemm(m, x_hi, x_lo, ly.qkv, Ti, EPI_BIAS_F32, nullptr, ws.qkv, nullptr, nullptr, st))) return rc;
@@ -678,6 +737,18 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
       else if (dh == 32) rc = launch_attention<32>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
       else rc = launch_attention<16>(att_grid, ws.qkv, (const long long*)mask, L, H, heads, scale_log2e, ws.ctx_hi, ws.ctx_lo, st);
       if (rc) return rc;
+    }
+    if (tail) {
+      gather_cls_kernel<<<n_seq, 256, 0, st>>>(ws.ctx_hi, ws.ctx_lo, ws.x, L, H, ws.cctx_hi, ws.cctx_lo, ws.cx);
+      CAPR_CHECK_CUDA(cudaGetLastError());
+      if ((rc = gemm(m, cc_hi, cc_lo, ly.attn_out, n_seq, EPI_BIAS_RESID_F32, ws.cx, ws.cy, nullptr, nullptr, st))) return rc;
+      ln_kernel<<<cls_row_blocks, 256, 0, st>>>(ws.cy, n_seq, H, ly.ln1_g, ly.ln1_b, m->cfg.ln_eps, ws.cx, ws.cx_hi, ws.cx_lo);
+      CAPR_CHECK_CUDA(cudaGetLastError());
+      if ((rc = gemm(m, cx_hi, cx_lo, ly.ffn1, n_seq, EPI_BIAS_GELU_SPLIT, nullptr, nullptr, ws.cffn_hi, ws.cffn_lo, st))) return rc;
+      if ((rc = gemm(m, cf_hi, cf_lo, ly.ffn2, n_seq, EPI_BIAS_RESID_F32, ws.cx, ws.cy, nullptr, nullptr, st))) return rc;
+      ln_kernel<<<cls_row_blocks, 256, 0, st>>>(ws.cy, n_seq, H, ly.ln2_g, ly.ln2_b, m->cfg.ln_eps, ws.cx, ws.cx_hi, ws.cx_lo);
+      CAPR_CHECK_CUDA(cudaGetLastError());
+      break;
     }
     if ((rc = gemm(m, c_hi, c_lo, ly.attn_out, Ti, EPI_BIAS_RESID_F32, ws.x, ws.y, nullptr, nullptr, st))) return rc;
     ln_kernel<<<row_blocks, 256, 0, st>>>(ws.y, Ti, H, ly.ln1_g, ly.ln1_b, m->cfg.ln_eps, ws.x, ws.x_hi, ws.x_lo);
@@ -689,7 +760,9 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
     if ((rc = emit_hidden(l + 1))) return rc;
   }
   if (logits) {
-    pooler_classifier_kernel<<<n_seq, 256, 2 * H * sizeof(float), st>>>(ws.x, L, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b, m->cfg.n_labels, logits);
+    // (CLS-only tail: the final hidden [CLS] rows are the compact buffer, one row per sequence)
+    pooler_classifier_kernel<<<n_seq, 256, 2 * H * sizeof(float), st>>>(cls_only ? ws.cx : ws.x, cls_only ? 1 : L, H, m->pool_w, m->pool_b, m->cls_w, m->cls_b,
+                                                                        m->cfg.n_labels, logits);
     CAPR_CHECK_CUDA(cudaGetLastError());
   }
   return CAPR_OK;
@@ -748,7 +821,7 @@ size_t capr_parade_workspace_bytes(capr_bert_t agg, int B, int P) {
   Model* m = (Model*)agg;
   if (!m || B <= 0 || P <= 0) return 0;
   const size_t rows = (size_t)B * (P + 1);
-  return carve(m->cfg, rows, nullptr, nullptr) + parade_extra_bytes(m->cfg, rows);
+  return carve(m->cfg, rows, (size_t)B, nullptr, nullptr) + parade_extra_bytes(m->cfg, rows);
 }
 
 int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, int L, const float* initial_cls, const float* pos_emb,
@@ -764,7 +837,7 @@ int capr_parade_head(capr_bert_t agg, const float* last_hidden, int B, int P, in
   CAPR_REQUIRE(((uintptr_t)workspace & 255) == 0, CAPR_ERR_BAD_POINTER, "%s: workspace must be 256-byte aligned", fn);
   const int H = m->cfg.hidden;
   const size_t rows = (size_t)B * (P + 1);
-  const size_t enc = carve(m->cfg, rows, nullptr, nullptr);
+  const size_t enc = carve(m->cfg, rows, (size_t)B, nullptr, nullptr);
   CAPR_REQUIRE(workspace_bytes >= enc + parade_extra_bytes(m->cfg, rows), CAPR_ERR_BAD_SHAPE, "%s: workspace too small (capr_parade_workspace_bytes)", fn);
   unsigned char* p = (unsigned char*)workspace + enc;
   float* merged = (float*)p;

@@ -41,6 +41,9 @@ struct Attn2Args {
   __nv_bfloat16* ctx_lo;
   int debug;              // profiling only (CAPR_ATTN_DEBUG; results invalid): 1 no softmax math, 2 no P.V MMAs, 4 no K/V reloads, 8 no Q.K MMAs
   long long* trace;       // profiling only (CAPR_ATTN_TRACE): CTA 0 of the grid records clock64 stamps, [role][event] (see TR_* below)
+  int q_blocks;           // attention_tc4_kernel only: 256-query blocks per (sequence, head) to compute, 0 = all of them.  The last
+                          // encoder layer of a classification forward needs the [CLS] row alone (ptBERTMaxP.py:82 reads logits of
+                          // the pooled row 0), i.e. block 0.
 };
 
 // trace layout: 64 slots per role; roles: 0 producer, 1 MMA, 2 softmax block 0 (warp 4), 3 softmax block 1 (warp 8)

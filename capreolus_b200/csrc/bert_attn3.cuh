@@ -48,7 +48,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
   int* ntiles = reinterpret_cast<int*>(tmem_slot + 2);  // [2 item parities]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int qblocks = (a.L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ);
+  const int all_qblocks = (a.L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ);
+  const int qblocks = (a.q_blocks > 0 && a.q_blocks < all_qblocks) ? a.q_blocks : all_qblocks;
   const int n_items = a.n_seq * a.heads * qblocks;
 
   if (tid == 0) {

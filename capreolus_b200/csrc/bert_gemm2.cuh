@@ -13,8 +13,12 @@
 //                                       cleared); the leader's producer posts expect_tx for both CTAs' bytes.
 //   MMA issuer (warp 1 of the leader)   waits `full`, issues tcgen05.mma.cta_group::2, frees the stage in BOTH CTAs with
 //                                       tcgen05.commit ... multicast::cluster (mask 0b11), publishes accumulators likewise.
-//   epilogue (warps 4-7 of both CTAs)   each CTA drains ITS 128 accumulator rows (its own TMEM); all 8 warps of the pair
-//                                       arrive on the leader's acc_empty barrier (remote mbarrier.arrive for the peer).
+//   epilogue (warps 4-11 of both CTAs)  each CTA drains ITS 128 accumulator rows (its own TMEM): two warps per TMEM lane
+//                                       quarter, one per 128-column half of the tile (the erf-GELU + bf16 split of FFN1 costs
+//                                       ~45 instructions per element: with one warp per scheduler the epilogue of a K = 768
+//                                       tile outlasted its 18.4 k cycles of MMAs, launch list r01_v10: 784 us vs 606 us for
+//                                       FFN2); all 16 warps of the pair arrive on the leader's acc_empty barrier (remote
+//                                       mbarrier.arrive for the peer).
 //   TMEM                                tcgen05.alloc.cta_group::2 by warp 2 of both CTAs; cluster barriers bracket the kernel.
 #pragma once
 #include "bert_gemm.cuh"
@@ -22,6 +26,7 @@
 namespace capr {
 namespace bert {
 
+constexpr int G2_THREADS = 384;                  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int G2_BN = 256;                       // columns per pair tile (UMMA N); each CTA holds half of the B tile
 constexpr int G2_B_HALF_BYTES = (G2_BN / 2) * BK * 2;  // 16 KB
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
@@ -78,7 +83,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 
 // tm_b_*: maps of the weight planes with a {64, 128} box (half of the pair's B tile per CTA).
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
              const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmArgs g) {
   using S = Gemm2Smem<MODE>;
@@ -114,7 +119,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&acc_full[b], 1);
-      tc::mbar_init(&acc_empty[b], 8);  // 4 epilogue warps in each CTA of the pair
+      tc::mbar_init(&acc_empty[b], 16);  // 8 epilogue warps in each CTA of the pair
     }
     tc::fence_barrier_init();
   }
@@ -190,6 +195,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant_
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: each drains its own 128 rows) =====================
     const int quarter = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * (G2_BN / 2);  // this warp's 128-column half of the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < n_tiles; t += n_pairs) {
@@ -198,7 +204,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant_
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * G2_BN) + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < G2_BN; c += 32) {
+      for (int c = c_begin; c < c_begin + G2_BN / 2; c += 32) {
         float v[32];
         tc::tmem_ld_32x32(t_row + (uint32_t)c, v);
         tc::tmem_ld_wait();

@@ -42,12 +42,18 @@ class CEDRKNRM_Class(nn.Module):
         self.extractor = extractor
         self.config = config
         pretrained = config["pretrained"]
-        if isinstance(pretrained, dict):
+        if isinstance(pretrained, dict) and pretrained.get("model_type") == "electra":
+            # offline extension: an ElectraConfig dict -> random-init Electra encoder
+            cfg_kw = {k: v for k, v in pretrained.items() if k != "model_type"}
+            self.bert = transformers.ElectraModel(transformers.ElectraConfig(**{**cfg_kw, "hidden_dropout_prob": config["hidden_dropout_prob"],
+                                                                              "output_hidden_states": True}))
+        elif isinstance(pretrained, dict):
             # offline extension: a BertConfig dict -> random-init encoder (there is no network for checkpoints here)
             self.bert = transformers.BertModel(transformers.BertConfig(**{**pretrained, "hidden_dropout_prob": config["hidden_dropout_prob"],
                                                                         "output_hidden_states": True}))
-        elif "electra" in pretrained:
-            raise ValueError(f"capreolus_b200 CEDRKNRM: {pretrained!r} is not a BERT encoder (Electra variants are out of scope)")
+        elif isinstance(pretrained, str) and "electra" in pretrained:  # CEDRKNRM.py:20-27 (the reference default)
+            name = {"electra-base-msmarco": "Capreolus/electra-base-msmarco", "electra-base": "google/electra-base-discriminator"}.get(pretrained, pretrained)
+            self.bert = transformers.ElectraModel.from_pretrained(name, hidden_dropout_prob=config["hidden_dropout_prob"], output_hidden_states=True)
         elif pretrained == "bert-base-msmarco":
             self.bert = transformers.BertModel.from_pretrained("Capreolus/bert-base-msmarco", hidden_dropout_prob=config["hidden_dropout_prob"],
                                                                output_hidden_states=True)

@@ -90,7 +90,7 @@ class ConvKNRM_class(nn.Module):
 
     def _run(self, sentence, query_sentence, want_feats=False):
         _lib.require_cuda(sentence, query_sentence)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
             raise NotImplementedError("capreolus_b200 ConvKNRM: only inference (torch.no_grad / requires_grad=False) is implemented")
         q, d = _ids(query_sentence), _ids(sentence)
         B, Q = q.shape

@@ -40,7 +40,7 @@ class DRMMTKS_class(nn.Module):
             # DRMMTKS.py:59 hands the int64 token ids to _term_gate, whose TV branch applies Linear(E,1) to them (l.43):
             # the reference raises there, so there is no behaviour to reproduce
             raise ValueError("Invalid value for gateType: DRMMTKS supports gateType='IDF' only (the reference's 'TV' branch cannot run)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
             raise NotImplementedError("capreolus_b200 DRMMTKS: only inference (torch.no_grad / requires_grad=False) is implemented")
         q, d = _ids(query), _ids(doc)
         B, Q = q.shape

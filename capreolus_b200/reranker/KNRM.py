@@ -77,7 +77,7 @@ class KNRM_class(nn.Module):
 
     def forward(self, doctoks, querytoks, query_idf):
         _lib.require_cuda(doctoks, querytoks)
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())  # eval mode: inference kernel
         if needs_grad:
             if self.embedding.weight.requires_grad:
                 raise NotImplementedError("capreolus_b200 KNRM: finetune=True (gradient to the embedding table) is not implemented")

@@ -53,7 +53,7 @@ class PACRR_class(nn.Module):
 
     def _run(self, sentence, query_sentence, query_idf, want_topk=False):
         _lib.require_cuda(sentence, query_sentence)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
             raise NotImplementedError("capreolus_b200 PACRR: only inference (torch.no_grad / requires_grad=False) is implemented")
         p = self.p
         q, d = _ids(query_sentence), _ids(sentence)

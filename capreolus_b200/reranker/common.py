@@ -146,34 +146,35 @@ class RbfKernelBank(torch.nn.Module):
         return self._cache
 
 
-def pair_softmax_loss(pos_neg_scores, *args, **kwargs):
-    """capreolus/reranker/common.py:96-98"""
-    scores = torch.stack(pos_neg_scores, dim=1)
-    return torch.mean(1.0 - scores.softmax(dim=1)[:, 0])
+class _PairLoss(torch.autograd.Function):
+    """A pairwise loss kernel that returns the loss and d loss / d score in one launch (``capr_pair_hinge`` / ``capr_pair_softmax``)."""
 
-
-class _PairHinge(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, neg):
+    def forward(ctx, pos, neg, entry):
         _lib.require_cuda(pos, neg)
         pos, neg = pos.contiguous().float(), neg.contiguous().float()
         B = pos.shape[0]
         loss = torch.empty(1, dtype=torch.float32, device=pos.device)
         gpos, gneg = torch.empty_like(pos), torch.empty_like(neg)
-        _lib.check(_lib.lib().capr_pair_hinge(pos.data_ptr(), neg.data_ptr(), B, loss.data_ptr(), gpos.data_ptr(), gneg.data_ptr(),
-                                             _lib.current_stream(pos.device)))
+        _lib.check(getattr(_lib.lib(), entry)(pos.data_ptr(), neg.data_ptr(), B, loss.data_ptr(), gpos.data_ptr(), gneg.data_ptr(),
+                                              _lib.current_stream(pos.device)))
         ctx.save_for_backward(gpos, gneg)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         gpos, gneg = ctx.saved_tensors
-        return g * gpos, g * gneg
+        return g * gpos, g * gneg, None
+
+
+def pair_softmax_loss(pos_neg_scores, *args, **kwargs):
+    """``pair_softmax_loss`` (capreolus/reranker/common.py:96-98): mean(1 - softmax(stack([pos, neg], 1), 1)[:, 0])."""
+    return _PairLoss.apply(pos_neg_scores[0], pos_neg_scores[1], "capr_pair_softmax")
 
 
 def pair_hinge_loss(pos_neg_scores, *args, **kwargs):
     """``pair_hinge_loss`` (capreolus/reranker/common.py:7,101-103): MarginRankingLoss(margin=1, mean), target +1."""
-    return _PairHinge.apply(pos_neg_scores[0], pos_neg_scores[1])
+    return _PairLoss.apply(pos_neg_scores[0], pos_neg_scores[1], "capr_pair_hinge")
 
 
 def device_pointer_array(tensors):

@@ -43,8 +43,13 @@ class BertEngine:
 
     def __init__(self, hf_model, precision="bf16x3", max_seqs_per_call=128):
         cfg = hf_model.config
-        if cfg.model_type != "bert":
-            raise ValueError(f"capreolus_b200 ptBERTMaxP supports BERT encoders only, got {cfg.model_type!r}")
+        # Electra's encoder (CEDR-KNRM's default, CEDRKNRM.py:20-27) is the BERT encoder under other parameter names as long as
+        # there is no embedding projection (embedding_size == hidden_size: electra-base); it has no pooler
+        electra = cfg.model_type == "electra"
+        if cfg.model_type not in ("bert", "electra"):
+            raise ValueError(f"capreolus_b200 encoder engine supports BERT / Electra encoders only, got {cfg.model_type!r}")
+        if electra and getattr(cfg, "embedding_size", cfg.hidden_size) != cfg.hidden_size:
+            raise ValueError("capreolus_b200 encoder engine: Electra with an embedding projection (embedding_size != hidden_size) is not implemented")
         if getattr(cfg, "hidden_act", "gelu") != "gelu":
             raise ValueError("capreolus_b200 ptBERTMaxP: only hidden_act='gelu' (erf) is implemented")
         if getattr(cfg, "position_embedding_type", "absolute") != "absolute":
@@ -52,6 +57,13 @@ class BertEngine:
         state = hf_model.state_dict()
         headless = "classifier.weight" not in state  # a bare BertModel (CEDR-KNRM): no classification head
         keys = bert_weight_keys(cfg.num_hidden_layers, "" if headless else "bert.", classifier=not headless)
+        if electra and not headless:
+            raise ValueError("capreolus_b200 encoder engine: Electra classification heads are not implemented (hidden states only)")
+        some = state[keys[0]]
+        _lib.require_cuda(some)
+        H = cfg.hidden_size
+        if electra:  # ElectraModel has no pooler: zeros (a headless engine never evaluates it)
+            state = {**state, "pooler.dense.weight": torch.zeros((H, H), device=some.device), "pooler.dense.bias": torch.zeros(H, device=some.device)}
         tensors = [state[k].detach().float().contiguous() for k in keys]
         _lib.require_cuda(*tensors)
         self.device = tensors[0].device

@@ -114,10 +114,17 @@ def bert_batch(n: int, seqlen: int = 512, qlen: int = 32, vocab: int = BERT_VOCA
                ragged: bool = True) -> dict:
     """The BERT set: ``[CLS] q(qlen) [SEP] d [SEP]`` padded to ``seqlen``; arrays are ``[n, P, L] int64``."""
     rng = np.random.default_rng(seed)
+    lo = min(1000, vocab // 2)
+    if not ragged:  # full-length sequences (throughput runs): vectorised, 125 000 sequences in a second instead of a Python loop
+        ids = rng.integers(lo, vocab, size=(n, numpassages, seqlen), dtype=np.int64)
+        ids[..., 0], ids[..., qlen + 1], ids[..., seqlen - 1] = CLS, SEP, SEP
+        mask = np.ones_like(ids)
+        seg = np.zeros_like(ids)
+        seg[..., qlen + 2:] = 1
+        return {"pos_bert_input": ids, "pos_mask": mask, "pos_seg": seg}
     ids = np.zeros((n, numpassages, seqlen), dtype=np.int64)
     mask = np.zeros_like(ids)
     seg = np.zeros_like(ids)
-    lo = min(1000, vocab // 2)
     for b in range(n):
         for p in range(numpassages):
             max_d = seqlen - qlen - 3

@@ -211,6 +211,10 @@ int capr_rank_by_query(const float* scores, const int64_t* seg_off, int n_querie
  * grad_pos/grad_neg [B] (nullable) = d loss / d score. */
 int capr_pair_hinge(const float* pos, const float* neg, int B, float* loss, float* grad_pos, float* grad_neg,
                     capr_stream_t stream);
+/* pair_softmax_loss (capreolus/reranker/common.py:96-98; trainer config softmaxloss=True, trainer/pytorch.py:220-223):
+ * loss[0] = mean(1 - softmax([pos, neg], dim=1)[:, 0]); grad_pos / grad_neg [B] (nullable) = d loss / d score. */
+int capr_pair_softmax(const float* pos, const float* neg, int B, float* loss, float* grad_pos, float* grad_neg,
+                      capr_stream_t stream);
 
 /* ---- monoBERT / BERT-MaxP encoder -------------------------------------------------------------------
  * PTBERTMaxP_Class.predict_step (capreolus/reranker/ptBERTMaxP.py:67-96) calls

@@ -196,6 +196,41 @@ def test_cedrknrm_doc_chunking_is_invisible():
         rr.test(b)
 
 
+def test_cedrknrm_electra_encoder():
+    """CEDR-KNRM's reference default encoder is Electra (CEDRKNRM.py:20-27).  electra-base has no embedding projection, so its
+    encoder is the BERT encoder under other names: the engine's hidden states are checked against HF ``ElectraModel`` (the module
+    the reference calls) on the CPU, and the scores against the oracle's CEDR-KNRM forward on the same state."""
+    import copy
+
+    from capreolus_b200 import reranker as R, synthetic
+    from oracle import restated
+
+    P, L, maxqlen, N = 3, 48, 6, 5
+    ecfg = dict(model_type="electra", hidden_size=64, embedding_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                vocab_size=1000, max_position_embeddings=64)
+    torch.manual_seed(21)
+    rr = R.CEDRKNRM(dict(pretrained=ecfg, simmat_layers=[0, 1, 2], combine_hidden=16, cls="avg"), provide={"extractor": BertExtractor(P, L, maxqlen)})
+    model = rr.build_model().eval()
+    assert model.bert.config.model_type == "electra"
+    cpu_model = copy.deepcopy(model.bert).eval()
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = {k: torch.from_numpy(v) for k, v in synthetic.cedr_batch(N, P, L, maxqlen, vocab=1000, seed=23).items()}
+    flat = lambda t: t.reshape(N * P, L)
+    with torch.no_grad():
+        hf = cpu_model(flat(batch["pos_bert_input"]), attention_mask=flat(batch["pos_mask"]), token_type_ids=flat(batch["pos_seg"])).hidden_states
+        want = restated.cedrknrm_forward(state, batch["pos_bert_input"], batch["pos_mask"], batch["pos_seg"], 4, maxqlen, [0, 1, 2], "avg", 16).view(-1).numpy()
+    model.to(DEV)
+    gb = {k: v.to(DEV) for k, v in batch.items()}
+    hs = model.engine().hidden_states(flat(gb["pos_bert_input"]), flat(gb["pos_mask"]), flat(gb["pos_seg"]), [0, 1, 2]).cpu().numpy()
+    real = flat(batch["pos_mask"]).numpy().astype(bool).reshape(-1)  # HF leaves garbage-free but differently-attended pad rows: compare real tokens
+    for i in range(3):
+        np.testing.assert_allclose(hs[i][real], hf[i].reshape(N * P * L, -1).numpy()[real], atol=2e-3)
+    scores = rr.test(gb).cpu().numpy()
+    assert rel_err(scores, want, floor=1e-2) < TOL
+    with pytest.raises(ValueError):  # an embedding projection is not implemented
+        R.CEDRKNRM(dict(pretrained={**ecfg, "embedding_size": 32}), provide={"extractor": BertExtractor(P, L, maxqlen)}).build_model().to(DEV).engine()
+
+
 # ---- SURVEY.md §8(f) rank 2: PARADE --------------------------------------------------------------------------------------
 def _build_parade(name):
     import json

@@ -145,6 +145,64 @@ def test_drmm_histogram_matches_reference(shape, engine):
     assert np.all(np.abs(counts_got[:, :, 28] - c32[:, :, 28]) <= counts_got[:, :, 29] - 1 + 1e-6)
 
 
+@pytest.mark.parametrize("shape", ["full", "small"])
+def test_drmm_scores_vs_fp32_reference_lie_in_the_exact_match_envelope(shape):
+    """Score-level statement of how far the CUDA path sits from the PLAIN fp32 reference (`default/pos`, not `pos64`) on the zipf
+    PARITY set.  The only difference is where each exact match (identical in-vocabulary query / doc token) lands: the reference's
+    fp32 self-cosine is 1 +- 1 ulp by rounding noise, so `s < 1.0` (DRMM.py:63-65) puts it in or out of bin 28 by coin flip; the
+    kernel always counts it in.  For every pair the fp32 reference score must therefore lie in the interval spanned by moving, per
+    query row, 0..n_exact of the kernel's bin-28 counts out of that bin (gates are >= 0 and do not depend on the histogram).  Also
+    reports which fraction of the pairs agrees with the fp32 reference within 1e-3 outright."""
+    import json
+    import os
+
+    g = load_golden(f"drmm_{shape}")
+    rr, model = _build("DRMM", g, "default", DRMM_CFG["default"])
+    b = _batch(g)
+    st = {k: v.detach().cpu().double() for k, v in model.state_dict().items() if "embedding" not in k}
+    frac = {}
+    for side, doc_key in (("pos", "posdoc"), ("neg", "negdoc")):
+        with torch.no_grad():
+            got = model(b[doc_key], b["query"], b["query_idf"]).view(-1).cpu().numpy().astype(np.float64)
+            hist = model._hist_map(b["query"], b[doc_key]).cpu().double()  # [B,Q,30] = log(count + 1)
+        counts = torch.round(torch.exp(hist)) - 1.0
+        n_exact = counts[:, :, 29].clone()  # the exact-match slot: identical tokens (the disjoint rows have none)
+        Bn, Qn, _ = counts.shape
+        query = b["query"].cpu()
+        q_mask = (query != 0).double()
+        logits = b["query_idf"].cpu().double() * st["gates.weight"].view(()) + (1 - q_mask) * -1e7
+        gate = torch.softmax(logits, dim=1)  # [B,Q]
+
+        def z_of(cnt):  # ffw on log(count + 1)   (DRMM.py:71-76,106)
+            h = torch.log(cnt + 1.0)
+            z = torch.tanh(h @ st["ffw.0.weight"].T + st["ffw.0.bias"])
+            return torch.tanh(z @ st["ffw.2.weight"].T + st["ffw.2.bias"]).reshape(Bn, Qn)
+
+        z_lo = z_hi = z_of(counts)
+        for k in range(1, int(n_exact.max()) + 1):  # k exact matches of the row fall out of bin 28
+            moved = counts.clone()
+            take = torch.clamp(torch.full_like(n_exact, float(k)), max=n_exact)
+            moved[:, :, 28] -= take
+            zk = z_of(moved)
+            z_lo, z_hi = torch.minimum(z_lo, zk), torch.maximum(z_hi, zk)
+        w, bo = float(st["output_layer.weight"].view(())), float(st["output_layer.bias"].view(()))
+        a = (gate * z_lo).sum(1).numpy() * w + bo
+        c = (gate * z_hi).sum(1).numpy() * w + bo
+        lo, hi = np.minimum(a, c), np.maximum(a, c)
+        ref32 = g[f"default/{side}"].astype(np.float64)
+        slack = 1e-3 * np.maximum(np.abs(ref32), 1e-3)
+        inside = (ref32 >= lo - slack) & (ref32 <= hi + slack)
+        assert inside.all(), (side, np.nonzero(~inside)[0][:8], ref32[~inside][:8], lo[~inside][:8], hi[~inside][:8])
+        assert np.all((got >= lo - slack) & (got <= hi + slack))  # the kernel's own score is the k = 0 corner
+        err = np.abs(got - ref32) / np.maximum(np.abs(ref32), 1e-3)
+        frac[side] = {"pairs": int(err.size), "within_1e-3_of_fp32_reference": float((err < 1e-3).mean()), "max_rel_err_vs_fp32_reference": float(err.max()),
+                      "pairs_with_exact_matches": int((n_exact.sum(1) > 0).sum()), "max_envelope_width_rel": float(((hi - lo) / np.maximum(np.abs(ref32), 1e-3)).max())}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/drmm_fp32_envelope_{shape}.json", "w") as f:
+        json.dump({"golden": f"tests/golden/drmm_{shape}.npz", "stats": frac}, f, indent=1)
+    print(shape, json.dumps(frac))
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("variant", list(PACRR_CFG))
 def test_pacrr_scores_match_reference(shape, variant, engine):

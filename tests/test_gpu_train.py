@@ -31,6 +31,26 @@ def test_hinge_loss_and_gradient():
     assert torch.allclose(pos.grad.cpu(), p2.grad) and torch.allclose(neg.grad.cpu(), n2.grad)
 
 
+def test_softmax_loss_and_gradient():
+    """pair_softmax_loss (common.py:96-98) on the device: value vs the golden made by the reference function, gradient vs torch autograd."""
+    from capreolus_b200.reranker.common import pair_softmax_loss
+
+    g = load_golden("losses")
+    pos = torch.from_numpy(g["pos"]).to(DEV).requires_grad_()
+    neg = torch.from_numpy(g["neg"]).to(DEV).requires_grad_()
+    loss = pair_softmax_loss([pos, neg])
+    np.testing.assert_allclose(loss.item(), g["softmax"], rtol=1e-6)
+    (3.0 * loss).backward()
+    p2 = torch.from_numpy(g["pos"]).requires_grad_()
+    n2 = torch.from_numpy(g["neg"]).requires_grad_()
+    (3.0 * torch.mean(1.0 - torch.stack([p2, n2], dim=1).softmax(dim=1)[:, 0])).backward()
+    np.testing.assert_allclose(pos.grad.cpu().numpy(), p2.grad.numpy(), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(neg.grad.cpu().numpy(), n2.grad.numpy(), rtol=1e-5, atol=1e-8)
+    # a large score gap must not overflow (max-subtracted like torch's softmax)
+    big = pair_softmax_loss([torch.tensor([200.0, -300.0], device=DEV), torch.tensor([-200.0, 300.0], device=DEV)])
+    np.testing.assert_allclose(big.item(), 0.5, rtol=1e-6)
+
+
 @pytest.mark.parametrize("disjoint", [False, True])
 @pytest.mark.parametrize("shape", [(6, 8, 40, 500, 50), (4, 32, 512, 3000, 300)])
 def test_knrm_gradients_match_autograd_through_the_oracle(shape, disjoint):
@@ -72,11 +92,15 @@ def test_knrm_gradients_match_autograd_through_the_oracle(shape, disjoint):
         assert float((p.grad.cpu() - want).abs().max()) <= 2e-3 * scale + 1e-6, (name, p.grad.cpu(), want)
 
 
-@pytest.mark.parametrize("setting", ["frozen", "disjoint"])
+@pytest.mark.parametrize("setting", ["frozen", "disjoint", "zipfgrad"])
 @pytest.mark.parametrize("shape,dims", [("small", (8, 40, 500, 50, 10)), ("full", (32, 512, 30000, 300, 0))])
 def test_knrm_loss_curve_matches_reference_trainer(shape, dims, setting):
     """niters=2 of the reference PytorchTrainer + reference KNRM (golden) vs the same loop on the CUDA path.
-    frozen: zipf triples, gradkernels=False; disjoint: no shared terms, gradkernels=True (see oracle/make_goldens.py)."""
+    frozen: zipf triples, gradkernels=False; disjoint: no shared terms, gradkernels=True; zipfgrad: the reference DEFAULT --
+    zipf triples with exact matches AND gradkernels=True -- where the reference's own kernels.10.{mu,sigma} (sigma=0.001, mu=1.0)
+    random-walk on fp32 rounding noise (DESIGN.md "Exact matches"): every parameter EXCEPT those two and the loss curve are
+    compared.  Measured on CPU with the kernel's snap-to-1.0 rule emulated through the oracle: losses within 4e-4, combine
+    weights within 2.3e-5 absolute, kernels 0-9 bit-identical; the bars below are 2e-3 / 5e-3 (see oracle/make_goldens.py)."""
     from capreolus_b200 import reranker as R, synthetic
     from capreolus_b200.trainer import PairwiseTrainer
 
@@ -87,9 +111,10 @@ def test_knrm_loss_curve_matches_reference_trainer(shape, dims, setting):
     table = synthetic.embedding_table(V, E, seed=tseed)
     n_triples = cfg["itersize"] * cfg["niters"]
     data = synthetic.train_triples(n_triples, Q, D, V, seed=cfg["seed"], disjoint=setting == "disjoint")
+    skip = ("kernels.kernels.10.mu", "kernels.kernels.10.sigma") if setting == "zipfgrad" else ()
     chk = np.array([int(data["query"].sum()), int(data["posdoc"].sum()), int(data["negdoc"].sum())])
     assert np.array_equal(chk, g[f"{shape_name}/data_checksum"]), "synthetic TRAIN set differs from the one the golden was made with"
-    rr = R.KNRM({"gradkernels": setting == "disjoint"}, provide={"extractor": Extractor(table, Q, D)})
+    rr = R.KNRM({"gradkernels": setting != "frozen"}, provide={"extractor": Extractor(table, Q, D)})
     model = rr.build_model()
     init = {k[len(f"{shape_name}/init/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"{shape_name}/init/")}
     model.load_state_dict(init, strict=False)
@@ -111,11 +136,22 @@ def test_knrm_loss_curve_matches_reference_trainer(shape, dims, setting):
     # of a kernel whose soft-TF is saturated at log(1e-6) for every document) random-walks on rounding noise in the
     # reference too.  With exact matches frozen out ("frozen") every scalar must agree; in "disjoint" at least 90 % must,
     # and none may be further apart than the 32 steps could carry it.
-    close, total = 0, 0
+    close, total, worst = 0, 0, {}
     for k, want in final.items():
+        if k in skip:
+            continue
+        worst[k] = float(np.abs(got[k] - want).max())
         ok = np.abs(got[k] - want) <= 5e-3 * np.abs(want) + 2e-4
         assert np.all(np.abs(got[k] - want) <= 2 * 32 * cfg["lr"]), k
         if setting == "frozen":
             assert ok.all(), (k, got[k], want)
         close, total = close + int(ok.sum()), total + ok.size
     assert close >= 0.9 * total, (close, total)
+    import json
+    import os
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/knrm_train_{shape_name}.json", "w") as f:
+        json.dump({"golden": f"tests/golden/knrm_train.npz::{shape_name}", "losses": losses, "reference_losses": [float(x) for x in g[f"{shape_name}/losses"]],
+                   "loss_rel_err": [float(abs(a - b) / abs(b)) for a, b in zip(losses, g[f"{shape_name}/losses"])], "params_within_bar": [close, total],
+                   "skipped": list(skip), "max_abs_param_deviation": worst}, f, indent=1)
