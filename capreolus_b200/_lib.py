@@ -49,6 +49,10 @@ SIGNATURES = {
     "capr_table_prepare_bf16": (c_int, [_f32p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "capr_knrm_forward_tc": (c_int, [_i64p, _i64p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, _f32p, _f32p, c_int,
                                      _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p]),
+    "capr_tf_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "capr_tf_dedup": (c_int, [_i64p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "capr_knrm_forward_tf": (c_int, [_i64p, _i64p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, _f32p, _f32p, c_int,
+                                     _f32p, _f32p, c_int, _f32p, _f32p, c_int, _f32p, _f32p, c_void_p, c_size_t, c_void_p]),
     "capr_drmm_forward": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
                                   c_int, c_int, _f32p, _f32p, c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, c_void_p]),
     "capr_drmm_forward_tc": (c_int, [_i64p, _i64p, _f32p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, _f32p, c_int, c_int, _f32p,
@@ -93,6 +97,7 @@ DEBUG_SIGNATURES = {
     "capr_debug_mma_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "capr_debug_ffma2_bench": (c_int, [c_int, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
+    "capr_debug_gather_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
 }
 
 

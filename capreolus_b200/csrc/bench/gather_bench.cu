@@ -1,0 +1,94 @@
+// Micro-benchmark (debug library only): the L2 -> SM row-gather rate of the KNRM-family producer, with nothing else in the kernel.
+//
+// Same access pattern as simtc3::producer_loop: 4 warps per SM copy 128-row units of a bf16 (hi, lo) table, one 64-element K atom
+// of one plane per 16 KB stage, with 16-byte cp.async (8 lanes per 128-byte row segment) into the SWIZZLE_128B layout and
+// cp.async.mbarrier.arrive.noinc on the stage's barrier; a consumer warp frees every stage as soon as it has landed.  bench.py
+// reports the product kernel's gather traffic against this rate as a second roofline (`roofline.l2_gather`): it is the ceiling of
+// THIS access pattern on THIS machine (zipf row ids over a 36 MB L2-resident table), which no amount of overlap can beat.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace capr {
+
+constexpr int GB_PROD_THREADS = 128;
+constexpr int GB_THREADS = GB_PROD_THREADS + 32;
+constexpr int GB_STAGE_BYTES = 128 * 128;
+constexpr int GB_MAX_STAGES = 13;
+
+__global__ void __launch_bounds__(GB_THREADS, 1) gather_bench_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int pitch,
+                                                                     const int* __restrict__ rows, int n_units, int n_stages) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[GB_MAX_STAGES], empty[GB_MAX_STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int atoms = (pitch + 63) / 64;
+  const int last_chunks = (pitch - (atoms - 1) * 64) / 8;
+  if (tid == 0) {
+    for (int i = 0; i < n_stages; ++i) tc::mbar_init(&full[i], GB_PROD_THREADS), tc::mbar_init(&empty[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp < 4) {
+    const int sub = tid & 7, rsub = tid >> 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      unsigned off[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) off[j] = (unsigned)rows[(size_t)u * 128 + rsub + 16 * j] * (unsigned)pitch + (unsigned)(sub * 8);
+      for (int a = 0; a < atoms; ++a) {
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          const __nv_bfloat16* tab = (plane == 0 ? hi : lo) + a * 64;
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t base = tc::smem_u32(ring + stage * GB_STAGE_BYTES);
+          if (a + 1 < atoms || sub < last_chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = rsub + 16 * j;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]) : "memory");
+            }
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&full[stage])) : "memory");
+          if (++stage == n_stages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x)
+      for (int i = 0; i < 2 * atoms; ++i) {
+        tc::mbar_wait(&full[stage], phase);
+        __syncwarp();
+        if ((tid & 31) == 0) tc::mbar_arrive(&empty[stage]);
+        if (++stage == n_stages) stage = 0, phase ^= 1;
+      }
+  }
+}
+
+}  // namespace capr
+
+using namespace capr;
+
+// rows: [n_rows] int32 table rows in [0, V); n_rows is truncated to a multiple of 128.  stages: 16 KB stages in flight per SM (2..13).
+extern "C" int capr_debug_gather_bench(const void* table_hi, const void* table_lo, int V, int pitch, const int* rows, int n_rows, int stages,
+                                       capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table_hi);
+  const char* fn = "capr_debug_gather_bench";
+  CAPR_REQUIRE(table_hi && table_lo && rows, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(V > 0 && pitch > 0 && pitch % 16 == 0 && pitch <= 320 && n_rows >= 128 && stages >= 2 && stages <= GB_MAX_STAGES, CAPR_ERR_BAD_SHAPE,
+               "%s: bad arguments V=%d pitch=%d n_rows=%d stages=%d", fn, V, pitch, n_rows, stages);
+  CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit offsets", fn);
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  const size_t smem = 1024 + (size_t)stages * GB_STAGE_BYTES;
+  CAPR_CHECK_CUDA(cudaFuncSetAttribute(gather_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_units = n_rows / 128;
+  gather_bench_kernel<<<n_units < sms ? n_units : sms, GB_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, rows,
+                                                                                               n_units, stages);
+  CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}

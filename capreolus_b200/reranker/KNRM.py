@@ -56,6 +56,7 @@ class KNRM_class(nn.Module):
         self.embedding = create_emb_layer(extractor.embeddings, non_trainable=not self.p["finetune"])
         self.simmat = SimilarityMatrix(self.embedding)
         self._prepared = self.simmat._prepared
+        self._tf_ws = None  # scratch of the term-frequency pre-pass (capr_tf_workspace_bytes), grown on demand
 
         channels = 1
         if config["singlefc"]:
@@ -91,6 +92,19 @@ class KNRM_class(nn.Module):
         fc2 = None if self.p["singlefc"] else self.combine[2]
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         E = self.embedding.weight.shape[1]
+        if common.use_tensor_cores(D, E) and mu.shape[0] <= 16 and common.ENGINE == "tc":
+            # engine 3: term-frequency documents, pooling straight from tensor memory (csrc/knrm_tc3.cu)
+            hi, lo = self._prepared.get_bf16()
+            lib = _lib.lib()
+            need = lib.capr_tf_workspace_bytes(B, D)
+            if self._tf_ws is None or self._tf_ws.numel() < need or self._tf_ws.device != q.device:
+                self._tf_ws = torch.empty(max(need, 256), dtype=torch.uint8, device=q.device)
+            _lib.check(lib.capr_knrm_forward_tf(
+                q.data_ptr(), d.data_ptr(), B, Q, D, hi.data_ptr(), lo.data_ptr(), hi.shape[0], E, hi.shape[1], mu.data_ptr(), sigma.data_ptr(),
+                mu.shape[0], fc1.weight.data_ptr(), fc1.bias.data_ptr(), hidden, _lib.ptr(fc2.weight if fc2 is not None else None),
+                _lib.ptr(fc2.bias if fc2 is not None else None), SCORETANH if self.p["scoretanh"] else 0, scores.data_ptr(), None,
+                self._tf_ws.data_ptr(), self._tf_ws.numel(), _lib.current_stream(q.device)))
+            return scores
         if common.use_tensor_cores(D, E) and mu.shape[0] <= 16:
             hi, lo = self._prepared.get_bf16()
             _lib.check(_lib.lib().capr_knrm_forward_tc(

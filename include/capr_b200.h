@@ -96,6 +96,22 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
                          const float* w1, const float* b1, int hidden, const float* w2, const float* b2, int flags,
                          float* scores, float* feats, capr_stream_t stream);
 
+/* Engine 3 (tensor cores, term-frequency documents, pooling from tensor memory; csrc/simtc3.cuh): same contract and outputs as
+ * capr_knrm_forward_tc.  A pre-pass rewrites every document as its (distinct token, count) list in first-occurrence order --
+ * KNRM's kernel sums run over all doc positions (KNRM.py:50), so identical tokens contribute identical terms -- and the scoring
+ * kernel gathers each distinct token once.  workspace: capr_tf_workspace_bytes(B, D) bytes hold all B documents at once; a
+ * smaller workspace (at least capr_tf_workspace_bytes(1, D)) makes the call loop over chunks of pairs.  256-byte aligned.
+ * Limits: Q <= 32, D <= 1024, pitch <= 320, K <= 16 (else CAPR_ERR_UNSUPPORTED -> capr_knrm_forward_tc / capr_knrm_forward). */
+size_t capr_tf_workspace_bytes(int B, int D);
+/* The pre-pass on its own: doc [B,D] int64 -> ids [B,D] int32 (the distinct tokens of each document in first-occurrence order,
+ * <pad> = 0 and OOV (< 0) ids included as tokens, 0 beyond n_distinct[b]), counts [B,D] uint16 (multiplicities, 0 beyond),
+ * n_distinct [B].  sum(counts[b]) == D; ids outside int32 are clamped like everywhere else. */
+int capr_tf_dedup(const int64_t* doc, int B, int D, int32_t* ids, uint16_t* counts, int32_t* n_distinct, capr_stream_t stream);
+int capr_knrm_forward_tf(const int64_t* query, const int64_t* doc, int B, int Q, int D, const void* table_hi,
+                         const void* table_lo, int V, int E, int pitch, const float* mu, const float* sigma, int K,
+                         const float* w1, const float* b1, int hidden, const float* w2, const float* b2, int flags,
+                         float* scores, float* feats, void* workspace, size_t workspace_bytes, capr_stream_t stream);
+
 /* ---- DRMM -----------------------------------------------------------------------------------------
  * DRMM_class.forward (capreolus/reranker/DRMM.py:101-116): _hist_map (41-81) + ffw + _term_gate (83-99).
  *   idf [B,Q] fp32; bin_ub [nbins] = torch.linspace(-1,1,nbins+1)[1:] (device, the exact fp32 values)
@@ -300,6 +316,11 @@ int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps, int grid,
  * scalar operand from the constant bank (mode 0, the form PACRR's conv uses), from vector registers (mode 1), or as plain FFMA
  * pairs (mode 2).  scratch: >= 64 + grid*256 floats. */
 int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long long* cycles, capr_stream_t stream);
+/* Debug micro-benchmark (csrc/bench/gather_bench.cu): the pure L2 -> SM row-gather rate of the KNRM-family producer's access
+ * pattern -- 128-row units of a bf16 (hi, lo) table of `pitch` elements per row, rows[n_rows] int32 in [0, V), `stages` 16 KB
+ * stages in flight per SM.  The caller times the launch; bytes moved = (n_rows rounded down to 128) * pitch * 2 planes * 2 B. */
+int capr_debug_gather_bench(const void* table_hi, const void* table_lo, int V, int pitch, const int32_t* rows, int n_rows, int stages,
+                            capr_stream_t stream);
 #endif /* CAPR_DEBUG_BUILD */
 
 #ifdef __cplusplus

@@ -22,15 +22,44 @@ def test_pipelined_predict_equals_direct_test(n, chunk):
     rr = R.KNRM(provide={"extractor": Extractor(synthetic.embedding_table(V, E, seed=0), Q, D)})
     rr.build_model().to(DEV).eval()
     host = {k: torch.from_numpy(v) for k, v in synthetic.throughput_batch(n, Q, D, V, seed=9).items()}
-    pb = PinnedBatch(host)
-    assert pb.n == n and pb.bytes_per_item == (Q + D) * 8 + Q * 4
-    pred = PipelinedPredictor(rr, DEV, chunk=chunk)
     with torch.no_grad():
         direct = rr.test({k: v.to(DEV) for k, v in host.items()}).cpu()
-    for _ in range(2):  # buffers are reused across calls
-        out = pred.predict(pb)
-        assert out.shape == (n,) and out.is_pinned()
-        assert torch.equal(out.cpu(), direct)
+    # ids travel as int16 when the vocabulary fits (default), as the reference's int64 with narrow_ids=False
+    for narrow, per_item in ((True, (Q + D) * 2 + Q * 4), (False, (Q + D) * 8 + Q * 4)):
+        pb = PinnedBatch(host, narrow_ids=narrow)
+        assert pb.n == n and pb.bytes_per_item == per_item
+        assert (pb.tensors["posdoc"].dtype == torch.int16) == narrow
+        pred = PipelinedPredictor(rr, DEV, chunk=chunk)
+        first = None
+        for _ in range(2):  # buffers are reused across calls
+            out = pred.predict(pb)
+            assert out.shape == (n,)
+            assert torch.equal(out.cpu(), direct)
+            if first is None:
+                first = out
+        first_copy = first.clone()
+        pred.predict(PinnedBatch({k: v.flip(0) for k, v in host.items()}))  # a later call must not overwrite earlier results
+        assert torch.equal(first, first_copy)
+
+
+def test_narrow_ids_keep_oov_signs_and_wide_vocabularies():
+    """capr_widen_ids sign-extends: negative (OOV) ids survive the int16 / int32 trip; ids beyond int16 select int32."""
+    from capreolus_b200 import reranker as R, synthetic
+    from capreolus_b200.predict import PinnedBatch, PipelinedPredictor
+
+    Q, D, V, E = 8, 40, 40000, 32
+    rr = R.KNRM(provide={"extractor": Extractor(synthetic.embedding_table(V, E, seed=0), Q, D)})
+    rr.build_model().to(DEV).eval()
+    small = {k: torch.from_numpy(v) for k, v in synthetic.parity_batch(12, Q, D, 3000, seed=5, oov=True).items()}  # has negative ids
+    assert int(small["query"].min()) < 0
+    wide = {k: v.clone() for k, v in small.items()}
+    wide["posdoc"][:, 0] = 39999  # does not fit int16
+    for host, want in ((small, torch.int16), (wide, torch.int32)):
+        pb = PinnedBatch(host)
+        assert pb.tensors["posdoc"].dtype == want and pb.tensors["query_idf"].dtype == torch.float32
+        with torch.no_grad():
+            direct = rr.test({k: v.to(DEV) for k, v in host.items()}).cpu()
+        assert torch.equal(PipelinedPredictor(rr, DEV, chunk=5).predict(pb).cpu(), direct)
 
 
 def test_table_is_rebuilt_when_the_embedding_changes():
