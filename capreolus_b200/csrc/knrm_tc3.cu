@@ -177,13 +177,16 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s.acc_empty[quarter]);
       }
-      g0 += units;
-      // hand the per-row partial sums to the finisher: red[warp][k][lane]
+      // hand the per-row partial sums to the finisher: red[slot][k][lane], slot = (PAIR-LOCAL unit index mod 4, column half) --
+      // the quarter that pooled the pair's unit u is (g0 + u) % 4, which depends on the pairs this CTA scored before; indexing
+      // the partials by u % 4 makes the order of the final sum, and therefore the bits of the score, a function of the pair alone
       tc::mbar_wait(s.red_empty, (uint32_t)((it & 1) ^ 1));
-      float* mine = s.red + warp * (KT + 1) * 32 + lane;
+      const int slot = ((quarter - g0) & 3) + 4 * chalf;  // g0 here = first global unit of the pair
+      float* mine = s.red + slot * (KT + 1) * 32 + lane;
 #pragma unroll
       for (int k = 0; k < KT; ++k) mine[k * 32] = S[k];
       mine[KT * 32] = rs;
+      g0 += units;
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(s.red_full);
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
     }
   } else {
     // ===================== finisher: lane = query row ======================================================================
-    // t_k = sum over the 8 pooling warps in a fixed order; live rows (cosine row-sum != 0, KNRM.py:51) contribute log(t_k + 1e-6);
+    // t_k = sum over the 8 partial-sum slots (pair-local unit index mod 4, column half) in a fixed order; live rows (cosine row-sum != 0, KNRM.py:51) contribute log(t_k + 1e-6);
     // R_k = butterfly sum over the rows (fixed order -> bit-reproducible); combine by lanes k < K.
     int it = 0;
     for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
