@@ -132,9 +132,14 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
       cc[k] = -0.5f * 1.4426950408889634f / (sg * sg);
     }
     int it = 0, g0 = 0;
+    const int tr_role = warp == 0 ? 2 : 3;
+    int tr_n = (lane == 0 && (warp == 0 || warp == 5)) ? 0 : 1024;
+    (void)tr_role, (void)tr_n;
     for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
       const int pp = it & 1;
+      SIM3_TR(tr_role, 20);
       tc::mbar_wait(&s.ids_full[pp], (uint32_t)((it >> 1) & 1));
+      SIM3_TR(tr_role, 21);
       const int nd = s.nd[pp];
       const int qi = s.qid[pp * QT + lane];
       const int units = units_of(nd);
@@ -145,16 +150,21 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
         const int g = g0 + u;
         if ((g & 3) != quarter) continue;
         tc::mbar_wait(&s.acc_full[quarter], (uint32_t)((g >> 2) & 1));
+        SIM3_TR(tr_role, 22);
         tc::tc_fence_after();
         const int live = live_cols(nd, u);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int col0 = chalf * 64 + c * 32;
-          if (col0 >= live) break;
+          if (col0 >= live || CAPR_DBG(pr.debug & 8)) break;
           const int doc0 = pp * pr.dcap + u * U_DOCS + col0;
           float v[32];
           load_cosines(tmem_base, quarter, col0, live, qi, s.did + doc0, v);
           const unsigned short* cw = s.cnt + doc0;
+          if (CAPR_DBG(pr.debug & 1)) {
+            rs += v[lane & 31];
+            continue;
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {  // (fully unrolled: v[] must stay in registers)
             const uint2 c4 = *reinterpret_cast<const uint2*>(cw + 4 * j4);  // 4 counts (uint16), warp-wide broadcast
@@ -176,11 +186,13 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s.acc_empty[quarter]);
+        SIM3_TR(tr_role, 23);
       }
       // hand the per-row partial sums to the finisher: red[slot][k][lane], slot = (PAIR-LOCAL unit index mod 4, column half) --
       // the quarter that pooled the pair's unit u is (g0 + u) % 4, which depends on the pairs this CTA scored before; indexing
       // the partials by u % 4 makes the order of the final sum, and therefore the bits of the score, a function of the pair alone
       tc::mbar_wait(s.red_empty, (uint32_t)((it & 1) ^ 1));
+      SIM3_TR(tr_role, 24);
       const int slot = ((quarter - g0) & 3) + 4 * chalf;  // g0 here = first global unit of the pair
       float* mine = s.red + slot * (KT + 1) * 32 + lane;
 #pragma unroll
@@ -198,8 +210,11 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
     // t_k = sum over the 8 partial-sum slots (pair-local unit index mod 4, column half) in a fixed order; live rows (cosine row-sum != 0, KNRM.py:51) contribute log(t_k + 1e-6);
     // R_k = butterfly sum over the rows (fixed order -> bit-reproducible); combine by lanes k < K.
     int it = 0;
+    int tr_n = lane == 0 ? 0 : 1024;
+    (void)tr_n;
     for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
       tc::mbar_wait(s.red_full, (uint32_t)(it & 1));
+      SIM3_TR(4, 30);
       float t[KT + 1];
 #pragma unroll
       for (int k = 0; k <= KT; ++k) {
@@ -233,6 +248,7 @@ __global__ void __launch_bounds__(simtc3::THREADS, 1) knrm_tc3_kernel(const Knrm
         if (a.flags & CAPR_KNRM_SCORETANH) out = tanhf(out);
         if (lane == 0) a.scores[pair] = out;
       }
+      SIM3_TR(4, 31);
     }
   }
   teardown(s, tmem_base, tid);
@@ -325,7 +341,11 @@ int capr_knrm_forward_tf(const int64_t* query, const int64_t* doc, int B, int Q,
     CAPR_CHECK_CUDA(cudaGetLastError());
     KnrmTc3Args a{};
     a.pr = simtc3::Problem{(const long long*)query + lo * Q, tf_ids, tf_cnt, tf_nd, n, Q, D, V, (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo,
-                           pitch, E, n_stages, n_qbufs, dcap};
+                           pitch, E, n_stages, n_qbufs, dcap, 0, nullptr};
+#ifdef CAPR_DEBUG_BUILD
+    if (const char* de = getenv("CAPR_SIM3_DEBUG")) a.pr.debug = atoi(de);
+    if (const char* te = getenv("CAPR_SIM3_TRACE")) a.pr.trace = (long long*)strtoull(te, nullptr, 10);
+#endif
     a.K = K, a.hidden = hidden, a.flags = flags, a.mu = mu, a.sigma = sigma, a.w1 = w1, a.b1 = b1, a.w2 = w2, a.b2 = b2;
     a.scores = scores ? scores + lo : nullptr;
     a.feats = feats ? feats + lo * K : nullptr;

@@ -59,7 +59,21 @@ struct Problem {
   const __nv_bfloat16* lo;
   int pitch, E;
   int n_stages, n_qbufs, dcap;  // shared-memory layout chosen on the host (dcap = D rounded up to 128)
+  int debug;                    // debug build only (CAPR_SIM3_DEBUG; results invalid): 1 no pooling math, 2 no MMAs, 4 no gathers, 8 no TMEM loads
+  long long* trace;             // debug build only (CAPR_SIM3_TRACE=<device pointer>): CTA 0 records (clock64 << 8 | tag) per role, 1024 slots each
 };
+
+// trace roles: 0 producer thread 0, 1 MMA lane 0, 2 pooling warp 0 lane 0, 3 pooling warp 5 lane 0, 4 finisher lane 0
+#ifdef CAPR_DEBUG_BUILD
+#define SIM3_TR(role, tag)                                                                                          \
+  do {                                                                                                              \
+    if (pr.trace && blockIdx.x == 0 && tr_n < 1024) pr.trace[(role) * 1024 + tr_n++] = (clock64() << 8) | (tag); \
+  } while (0)
+#else
+#define SIM3_TR(role, tag) \
+  do {                     \
+  } while (0)
+#endif
 
 struct Smem {
   unsigned char* ring;   // n_stages x 16 KB
@@ -195,10 +209,14 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     }
   };
   fetch_ids(blockIdx.x);
+  int tr_n = ptid == 0 ? 0 : 1024;
+  (void)tr_n;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int pp = it & 1;
     prod_barrier();  // every producer thread is done reading the previous pair's qrow / drow
+    SIM3_TR(0, 1);
     tc::mbar_wait(&s.ids_empty[pp], (uint32_t)(((it >> 1) & 1) ^ 1));  // pooling + MMA are done with the ids of pair it-2
+    SIM3_TR(0, 2);
     const int nd = nd_next;
     if (ptid < QT) {
       s.qid[pp * QT + ptid] = id_as_int(q_next);
@@ -216,12 +234,14 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     }
     tc::mbar_arrive(&s.ids_full[pp]);  // (release: the plain stores above are visible to the waiters)
     prod_barrier();
+    SIM3_TR(0, 3);
     fetch_ids(pair + gridDim.x);
     const int units = units_of(nd);
     // query block: per K atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
     const int b = pr.n_qbufs == 2 ? pp : 0;
     const int qn = pr.n_qbufs == 2 ? (it >> 1) : it;
     tc::mbar_wait(&s.q_empty[b], (uint32_t)((qn & 1) ^ 1));
+    SIM3_TR(0, 4);
     {
       const uint32_t qbase = tc::smem_u32(s.qbuf(b));
 #pragma unroll
@@ -237,7 +257,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
       }
     }
     cp_async_arrive_noinc(&s.q_full[b]);
+    SIM3_TR(0, 5);
     for (int u = 0; u < units; ++u) {
+      SIM3_TR(0, 6);
       const int n16 = mma_n(live_cols(nd, u));
       unsigned off[8];   // element offsets of this thread's 8 rows (V * pitch < 2^31 is checked on the host)
       unsigned live = 0;  // bit j: row j is a real table row
@@ -257,7 +279,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int r = rsub + 16 * j;
-              if (r < n16)
+              if (r < n16 && !CAPR_DBG(pr.debug & 4))
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
                              "r"(((live >> j) & 1u) << 4)
                              : "memory");
@@ -268,6 +290,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
         }
       }
     }
+    SIM3_TR(0, 7);
   }
   cp_async_commit();
   cp_async_wait<0>();  // nothing may still be landing in shared memory when the CTA tears down
@@ -279,9 +302,13 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   int stage = 0, it = 0, g = 0;
   uint32_t d_phase = 0;
+  int tr_n = lane == 0 ? 0 : 1024;
+  (void)tr_n;
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int pp = it & 1;
+    SIM3_TR(1, 10);
     tc::mbar_wait(&s.ids_full[pp], (uint32_t)((it >> 1) & 1));
+    SIM3_TR(1, 11);
     const int nd = s.nd[pp];
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&s.ids_empty[pp]);  // this warp only needs the count
@@ -289,10 +316,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
     const int b = pr.n_qbufs == 2 ? pp : 0;
     const int qn = pr.n_qbufs == 2 ? (it >> 1) : it;
     tc::mbar_wait(&s.q_full[b], (uint32_t)(qn & 1));
+    SIM3_TR(1, 12);
     const uint32_t qaddr = tc::smem_u32(s.qbuf(b));
     for (int u = 0; u < units; ++u, ++g) {
       const int buf = g & 3;
       tc::mbar_wait(&s.acc_empty[buf], (uint32_t)(((g >> 2) & 1) ^ 1));
+      SIM3_TR(1, 13);
       tc::tc_fence_after();
       const uint32_t idesc = tc::make_instr_desc(tc::FMT_BF16, 128, mma_n(live_cols(nd, u)));
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * U_DOCS);
@@ -300,9 +329,10 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
       for (int a = 0; a < atoms; ++a) {
         const uint64_t a_hi = tc::make_sw128_kmajor_desc(a_base + a * Q_ATOM_BYTES);
         const uint64_t a_lo = tc::make_sw128_kmajor_desc(a_base + a * Q_ATOM_BYTES + Q_PLANE_BYTES);
-        const int ksteps = min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
+        const int ksteps = CAPR_DBG(pr.debug & 2) ? 0 : min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
         // d_hi stage: q_hi.d_hi and q_lo.d_hi
         tc::mbar_wait(&s.d_full[stage], d_phase);
+        if (a == 0) SIM3_TR(1, 14);
         tc::tc_fence_after();
         {
           const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.stage(stage)));
@@ -338,6 +368,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
         if (u + 1 == units) tc::umma_commit(&s.q_empty[b]);
       }
       __syncwarp();
+      SIM3_TR(1, 15);
     }
   }
 }

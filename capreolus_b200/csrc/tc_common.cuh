@@ -40,10 +40,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park a waiting warp instead of having it spin: without it the producer / MMA
-// warps of the persistent kernels burned a third of the issue slots in try_wait loops (ncu source view of pacrr_tc3_kernel:
-// 290 k of 897 k stall samples sat on two spin branches executed 300 M times).
+// mbarrier wait.  CAPR_MBAR_HINT (compile time): 0 = plain try_wait spin loop; > 0 = try_wait with that suspend-time hint in
+// nanoseconds (the hardware may park the waiting warp instead of having it spin).  Round 1 used a 10 ms hint because the spinning
+// producer / MMA warps of the persistent kernels burned a third of the issue slots in try_wait loops (ncu source view of
+// pacrr_tc3_kernel); the round-2 clock64 trace of knrm_tc3_kernel (scripts/sim3_trace.py) then showed every BLOCKING wait costing
+// ~600 cycles of wake-up latency with that hint -- see DESIGN.md for the A/B.
+#ifndef CAPR_MBAR_HINT
+#define CAPR_MBAR_HINT 0x989680
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if CAPR_MBAR_HINT > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -51,8 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)
+      "r"(parity), "r"((uint32_t)CAPR_MBAR_HINT)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+#endif
 }
 
 // ---- TMA ------------------------------------------------------------------------------------------
