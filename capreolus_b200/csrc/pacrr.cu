@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   float* feat = s.extra;  // [QT][qterm]
   float* h1 = feat + QT * ((a.maxgram - a.mingram + 1) * a.kmax + (a.idf ? 1 : 0));
   float* h2 = h1 + MAX_COMBINE;
-  const uint32_t tmem_base = setup(s, tid);
+  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP, a.pr.group_arrive);
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc3_kernel(const Pacr
     tc::mbar_init(&conv_full[0], 1);
     tc::mbar_init(&conv_full[1], 1);
   }
-  const uint32_t tmem_base = setup(s, tid);  // fence.mbarrier_init + __syncthreads inside
+  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP, a.pr.group_arrive);  // fence.mbarrier_init + __syncthreads inside
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
@@ -532,7 +532,10 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   a.q = (const long long*)query; a.d = (const long long*)doc; a.idf = idf;
   a.B = B; a.Q = Q; a.D = D; a.V = V; a.pitch = pitch; a.mingram = mingram; a.maxgram = maxgram; a.F = nfilters;
   a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = tc_engine ? nullptr : (const float*)table;
-  if (tc_engine) a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E, 0};
+  if (tc_engine) {
+    a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E, 0};
+    a.pr.group_arrive = simtc::group_arrive_default();
+  }
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
   // Stage the filter taps in constant memory (stream-ordered device-to-device copies).  The constant bank is one per device, so
   // calls are serialised per device: a call on another stream (or thread) first waits for the event recorded behind the previous

@@ -92,8 +92,8 @@ class KNRM_class(nn.Module):
         fc2 = None if self.p["singlefc"] else self.combine[2]
         scores = torch.empty((B, 1), dtype=torch.float32, device=q.device)
         E = self.embedding.weight.shape[1]
-        if common.use_tensor_cores(D, E) and mu.shape[0] <= 16 and common.ENGINE == "tc":
-            # engine 3: term-frequency documents, pooling straight from tensor memory (csrc/knrm_tc3.cu)
+        if common.use_tensor_cores(D, E) and mu.shape[0] <= 16 and common.ENGINE == "tc3":
+            # engine 3 (opt-in): term-frequency documents, pooling straight from tensor memory (csrc/knrm_tc3.cu)
             hi, lo = self._prepared.get_bf16()
             lib = _lib.lib()
             need = lib.capr_tf_workspace_bytes(B, D)

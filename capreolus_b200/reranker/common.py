@@ -14,9 +14,10 @@ import torch
 from capreolus_b200 import _lib
 
 
-#: cosine-tile engine for inference: "tc" = tcgen05 tensor cores (table as bf16 hi/lo planes; KNRM: engine 3 = term-frequency
-#: documents pooled straight from tensor memory, csrc/simtc3.cuh), "tc2" = the round-1 tensor-core engine everywhere (A/B runs),
-#: "ffma" = fp32 CUDA cores.  Shapes the tensor-core kernels do not cover (maxdoclen > 1024, emb dim > 320, ...) use "ffma".
+#: cosine-tile engine for inference: "tc" = tcgen05 tensor cores (table as bf16 hi/lo planes; engine 2, csrc/simtc.cuh), "tc3" =
+#: KNRM on engine 3 (term-frequency documents, cosines pooled straight from tensor memory, csrc/simtc3.cuh + knrm_tc3.cu:
+#: parity-green, measured slower than engine 2 -- DESIGN.md; the other models stay on engine 2), "ffma" = fp32 CUDA cores.
+#: Shapes the tensor-core kernels do not cover (maxdoclen > 1024, emb dim > 320, ...) use "ffma".
 ENGINE = os.environ.get("CAPR_SIM_ENGINE", "tc")
 DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only (CAPR_DEBUG_SKIP_*): results invalid
 
@@ -24,7 +25,7 @@ DEBUG_FLAGS = int(os.environ.get("CAPR_DEBUG_FLAGS", "0"), 0)  # profiling only 
 def use_tensor_cores(D: int, E: int, max_doclen: int = 1024) -> bool:
     """KNRM / DRMM / DRMMTKS pool column-additively over 256-doc units, so their tensor-core kernels take maxdoclen <= 1024 (the
     reference extractor's default is 800); PACRR needs the whole 512-column tile with its halo (``max_doclen=512``)."""
-    return ENGINE in ("tc", "tc2") and D <= max_doclen and E <= 320
+    return ENGINE in ("tc", "tc3") and D <= max_doclen and E <= 320
 
 
 def create_emb_layer(weights, non_trainable=True):

@@ -99,7 +99,7 @@ def test_engine3_matches_oracle_identity_prepass_and_engine2(B, Q, D, V, E, monk
     model.to(DEV)
     with torch.no_grad():
         want = restated.knrm_forward(state, torch.from_numpy(table), cpu["posdoc"], cpu["query"]).view(-1).numpy()
-        monkeypatch.setattr(common, "ENGINE", "tc")
+        monkeypatch.setattr(common, "ENGINE", "tc3")
         got = rr.test(gpu).cpu().numpy()
         again = rr.test(gpu).cpu().numpy()
         monkeypatch.setenv("CAPR_KNRM_TF", "0")  # identity pre-pass: every position its own token
@@ -108,20 +108,27 @@ def test_engine3_matches_oracle_identity_prepass_and_engine2(B, Q, D, V, E, monk
         monkeypatch.setenv("CAPR_SIM3_QBUFS", "1")  # the other shared-memory layout: one query buffer, a deeper ring
         one_q = rr.test(gpu).cpu().numpy()
         monkeypatch.delenv("CAPR_SIM3_QBUFS")
-        monkeypatch.setattr(common, "ENGINE", "tc2")
+        monkeypatch.setattr(common, "ENGINE", "tc")
         e2 = rr.test(gpu).cpu().numpy()
+        monkeypatch.setenv("CAPR_SIM_ARRIVE", "noinc")  # engine 2 with the round-1 stage hand-off (per-thread cp.async.mbarrier.arrive.noinc)
+        e2_noinc = rr.test(gpu).cpu().numpy()
+        monkeypatch.delenv("CAPR_SIM_ARRIVE")
     assert rel_err(got, want) < TOL
     assert np.array_equal(got, again)  # bit-reproducible
     assert np.array_equal(got, one_q)  # the layout does not change the arithmetic
     assert rel_err(ident, want) < TOL
     assert rel_err(got, e2, floor=1e-3) < 1e-4  # both engines sit ~1e-6 from the reference
+    assert np.array_equal(e2, e2_noinc)  # the hand-off protocol does not change the arithmetic
 
 
 def test_engine3_variants_and_features(monkeypatch):
     """singlefc=False / scoretanh, K = 16 kernels (the KT = 16 instantiation) and the feature output."""
+    import importlib
+
     from capreolus_b200 import synthetic
     from oracle import restated
 
+    monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.common"), "ENGINE", "tc3")
     B, Q, D, V, E = 12, 32, 512, 3000, 300
     table = synthetic.embedding_table(V, E, seed=3)
     batch = synthetic.parity_batch(B, Q, D, V, seed=11, oov=True)
@@ -141,8 +148,11 @@ def test_engine3_variants_and_features(monkeypatch):
 def test_engine3_shards_and_chunked_workspace_are_bitwise_identical(monkeypatch):
     """A pair's score does not depend on which launch / chunk / CTA it lands in: slices of the batch, and a workspace that only
     holds a few pairs at a time (the call loops), give the bits of the single call."""
+    import importlib
+
     from capreolus_b200 import _lib, synthetic
 
+    monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.common"), "ENGINE", "tc3")
     B, Q, D, V, E = 700, 32, 512, 3000, 300
     table = synthetic.embedding_table(V, E, seed=0)
     gpu = {k: torch.from_numpy(v).to(DEV) for k, v in synthetic.throughput_batch(B, Q, D, V, seed=5).items()}

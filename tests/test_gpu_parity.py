@@ -67,10 +67,10 @@ def test_simmat_matches_reference(shape):
     assert np.all(sim[np.ones_like(sim, bool) & (d == 0)[:, None, :]] == 0)
 
 
-@pytest.fixture(params=["tc", "tc2", "ffma"])
+@pytest.fixture(params=["tc", "tc3", "ffma"])
 def engine(request, monkeypatch):
-    """Run a test once per cosine-tile engine (tcgen05 tensor cores: "tc" = the default, KNRM on engine 3 with term-frequency
-    documents pooled from tensor memory; "tc2" = the round-1 tensor-core engine for every model / fp32 CUDA cores)."""
+    """Run a test once per cosine-tile engine (tcgen05 tensor cores: "tc" = engine 2, the default; "tc3" = KNRM on engine 3 with
+    term-frequency documents pooled from tensor memory, the other models unchanged / fp32 CUDA cores)."""
     import importlib
 
     monkeypatch.setattr(importlib.import_module("capreolus_b200.reranker.common"), "ENGINE", request.param)
