@@ -344,7 +344,7 @@ def l2_gather_probe(dev):
         return {"error": str(exc)[:200]}
 
 
-def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None, rr_model=None):
+def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None, rr_model=None, warmup_pairs=0, skip_e2e=False):
     """Device-resident + end-to-end timing of one model at this rank's share of the work.  Returns the rank-0 dict (None elsewhere)."""
     import torch.distributed as dist
 
@@ -359,9 +359,14 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
     gpu = {k: v.to(dev) for k, v in host.items()}
     n_total = n * world
     with torch.no_grad():
-        for _ in range(warmup):
-            s = rr.test(gpu)
-            scores = gather_scores(s, n_total) if world > 1 else s
+        if 0 < warmup_pairs < n:  # full-size single-step runs (configs[3]: 125 000 BERT pairs per GPU): warm the kernels up on a slice
+            small = {k: v[:warmup_pairs] for k, v in gpu.items()}
+            for _ in range(warmup):
+                rr.test(small)
+        else:
+            for _ in range(warmup):
+                s = rr.test(gpu)
+                scores = gather_scores(s, n_total) if world > 1 else s
         # ---- device-resident timing: K steps, CUDA events on the launching stream, max over ranks --------------
         k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -380,25 +385,27 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
         elapsed_ms = ev0.elapsed_time(ev1)
         kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
         # ---- end to end: pinned host ids -> H2D -> score -> D2H of the scores, through the public predict API ------
-        pred = PipelinedPredictor(rr, dev, chunk=chunk, ramp=model_key not in ENCODERS)  # encoder models: H2D is negligible, keep full chunks
-        for _ in range(2):
-            pred.predict(pinned)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ctx.barrier()
-        sampler.active = True
-        e0.record()
-        for _ in range(steps):
-            out = pred.predict(pinned)
-            if world > 1:
-                gather_scores(out.to(dev, non_blocking=True), n_total)
-        e1.record()
-        ctx.barrier()
-        sampler.active = False
-        e2e_clocks = sampler.summary(reset=True)
-        e2e_ms = e0.elapsed_time(e1)
         mine = scores[rank * n:(rank + 1) * n] if world > 1 else scores
         check = not os.environ.get("CAPR_BENCH_NOCHECK")  # profiling runs against the debug library with CAPR_*_DEBUG switches produce invalid scores
-        assert not check or torch.equal(out.to(dev), mine), "pipelined predict != direct test"
+        e2e_ms, e2e_clocks = None, None
+        if not skip_e2e:
+            pred = PipelinedPredictor(rr, dev, chunk=chunk, ramp=model_key not in ENCODERS)  # encoder models: H2D is negligible, keep full chunks
+            for _ in range(2):
+                pred.predict(pinned)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.barrier()
+            sampler.active = True
+            e0.record()
+            for _ in range(steps):
+                out = pred.predict(pinned)
+                if world > 1:
+                    gather_scores(out.to(dev, non_blocking=True), n_total)
+            e1.record()
+            ctx.barrier()
+            sampler.active = False
+            e2e_clocks = sampler.summary(reset=True)
+            e2e_ms = e0.elapsed_time(e1)
+            assert not check or torch.equal(out.to(dev), mine), "pipelined predict != direct test"
         # ---- end to end from a packed, device-resident id store: only (query, doc) indices cross PCIe ----
         packed_ms = None
         if packed and model_key not in ENCODERS:
@@ -426,14 +433,15 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
             packed_ms = p0.elapsed_time(p1)
             assert not check or torch.equal(host_scores.to(dev), mine), "packed-store predict != direct test"
     # ---- per-rank numbers: the line reports the MAX (the contract) and min / median / max + the full list, so that a slow rank shows
-    mine_stats = [elapsed_ms, e2e_ms, kernel_ms, packed_ms or 0.0, pre_nccl or 0.0, float(clocks["sm_mhz"] or 0.0)]
+    mine_stats = [elapsed_ms, e2e_ms or 0.0, kernel_ms, packed_ms or 0.0, pre_nccl or 0.0, float(clocks["sm_mhz"] or 0.0)]
     per_rank = None
     if world > 1:
         t = torch.tensor(mine_stats, device=dev, dtype=torch.float64)
         allr = torch.empty((world, len(mine_stats)), device=dev, dtype=torch.float64)
         dist.all_gather_into_tensor(allr, t)
         allr = allr.cpu().numpy()
-        elapsed_ms, e2e_ms, kernel_ms, pm = (float(allr[:, i].max()) for i in range(4))
+        elapsed_ms, e2e_max, kernel_ms, pm = (float(allr[:, i].max()) for i in range(4))
+        e2e_ms = e2e_max if e2e_ms is not None else None
         packed_ms = pm if packed_ms is not None else None
         spread = lambda col: {"min": float(allr[:, col].min()), "median": float(np.median(allr[:, col])), "max": float(allr[:, col].max()),
                               "per_rank": [round(float(x), 4) for x in allr[:, col]]}
@@ -477,7 +485,7 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
         "vs_baseline": None, "dtype": "f32" if model_key not in ENCODERS else "bf16x3 (fp32 accumulate)", "data": "synthetic",
         "config": config_block(model_key, n, world),
         "roofline": roof,
-        "e2e": {"value": n_total * steps / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": pinned.bytes_per_item * n,
+        "e2e": {"value": (n_total * steps / (e2e_ms * 1e-3)) if e2e_ms else None, "unit": "pairs/s", "h2d_bytes_per_step": pinned.bytes_per_item * n,
                 "d2h_bytes_per_step": 4 * n, "api": "capreolus_b200.predict.PipelinedPredictor(reranker).predict(PinnedBatch(host batch))",
                 "host_id_dtypes": {k: str(v.dtype).replace("torch.", "") for k, v in pinned.tensors.items()},
                 "note": "token ids travel in the narrowest integer type that holds them (int16 for a 30k vocabulary; the reference ships int64) "
@@ -584,6 +592,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the monoBERT `secondary` block of the default (KNRM) line")
     ap.add_argument("--secondary-pairs", type=int, default=1024, help="monoBERT pairs per GPU per step in the `secondary` block")
+    ap.add_argument("--warmup-pairs", type=int, default=0, help="run the warm-up steps on the first N pairs only (full-size single-step runs, e.g. configs[3])")
+    ap.add_argument("--skip-e2e", action="store_true", help="device-resident timing only (profile runs of the full-size configs; the driver's default line keeps e2e)")
     args = ap.parse_args()
     args.pairs = args.pairs or DEFAULT_PAIRS[args.model]
     args.chunk = args.chunk or DEFAULT_CHUNK[args.model]
@@ -615,7 +625,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=ctx.dev)
 
-    line = measure(args.model, ctx, args.pairs, args.chunk, args.steps, args.warmup, pre_nccl=pre_nccl, rr_model=(rr, model))
+    line = measure(args.model, ctx, args.pairs, args.chunk, args.steps, args.warmup, pre_nccl=pre_nccl, rr_model=(rr, model), warmup_pairs=args.warmup_pairs,
+                   skip_e2e=args.skip_e2e, packed=not args.skip_e2e)
     if args.model == "knrm" and ctx.rank == 0 and ctx.world == 1 and not os.environ.get("CAPR_BENCH_NO_L2PROBE"):
         probe = l2_gather_probe(ctx.dev)
         if probe and "gbs" in probe:
