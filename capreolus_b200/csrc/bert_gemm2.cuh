@@ -223,8 +223,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant_
             for (int i = 0; i < 16; ++i) {
               float x0 = v[2 * i], x1 = v[2 * i + 1];
               if (g.epi == EPI_BIAS_GELU_SPLIT) {
-                x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));  // erf GELU (HF "gelu")
-                x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
+                x0 = gelu_erf(x0);  // erf GELU (HF "gelu")
+                x1 = gelu_erf(x1);
               }
               __nv_bfloat16 h0, l0, h1, l1;
               split_bf16(x0, h0, l0);

@@ -59,8 +59,11 @@ __device__ __forceinline__ float act(float x, int nonlin) { return nonlin == 1 ?
 // The 4 query rows of the warp are convolved together and every lane takes TWO doc columns per step (c and c + 32),
 // packed in the two halves of FFMA2 operands: a filter tap (a uniform-register scalar, broadcast by the instruction)
 // feeds 4 FFMA2 = 8 multiply-adds, and the windows of the 4 rows share their shared-memory loads.
+// ncols: conv positions of this doc tile that are eligible for the top-k (the whole tile, or -- doc tiling, D > 512 -- the positions
+// whose windows lie inside the tile); merge: fold the tile's top-k into the lists already in `feat` (second and later tiles).
 template <int N, int FT, int KM, int R>
-__device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int q0, int lane) {
+__device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int q0, int lane, int ncols,
+                                           bool merge) {
   constexpr int w_off = conv_w_slot(N), b_off = conv_b_slot(N);
   if (q0 >= a.Q) return;  // warp-uniform
   float top[R][KM];
@@ -68,7 +71,7 @@ __device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a,
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int k = 0; k < KM; ++k) top[r][k] = -INFINITY;
-  for (int c = lane; c < a.D; c += 64) {
+  for (int c = lane; c < ncols; c += 64) {
     float2 win[R + N - 1][N];  // .x: column c, .y: column c + 32 (inside the zero halo when past the doc)
 #pragma unroll
     for (int u = 0; u < R + N - 1; ++u)
@@ -102,7 +105,7 @@ __device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a,
     } else {
       for (int f = 0; f < F; ++f) one_filter(f);
     }
-    const bool second = c + 32 < a.D;
+    const bool second = c + 32 < ncols;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -124,46 +127,62 @@ __device__ __forceinline__ void ngram_rows(const float* sim, const PacrrArgs& a,
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (q0 + r >= a.Q) break;  // warp-uniform
+    float* out = feat + (q0 + r) * qterm + col0;
+    float old[KM];  // descending top-k of the earlier doc tiles
+#pragma unroll
+    for (int k = 0; k < KM; ++k) old[k] = (merge && k < a.kmax) ? out[k] : -INFINITY;
+    int taken = 0;  // how many of `old` have been emitted
     for (int k = 0; k < a.kmax; ++k) {
-      const float m = warp_max(top[r][0]);
+      const float m = warp_max(top[r][0]);  // largest value of this tile not emitted yet
+      float o = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KM; ++j) o = j == taken ? old[j] : o;
+      if (o >= m) {  // warp-uniform: the earlier tiles' next value wins; the tile's candidate stays for the next round
+        ++taken;
+        if (lane == 0) out[k] = o;
+        continue;
+      }
       const unsigned owners = __ballot_sync(0xffffffffu, top[r][0] == m);
       if (lane == (__ffs(owners) - 1)) {
 #pragma unroll
         for (int j = 0; j < KM - 1; ++j) top[r][j] = top[r][j + 1];
         top[r][KM - 1] = -INFINITY;
       }
-      if (lane == 0) feat[(q0 + r) * qterm + col0 + k] = m;
+      if (lane == 0) out[k] = m;
     }
   }
 }
 
 // 4 rows at a time for the windows the reference uses (n <= 3); 2 + 2 for the larger ones (register budget)
 template <int N, int FT, int KM>
-__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane) {
+__device__ __forceinline__ void ngram_pass(const float* sim, const PacrrArgs& a, int F, float* feat, int qterm, int col0, int warp, int lane, int ncols,
+                                           bool merge) {
   constexpr int ROWS = QT / (NT / 32);
   if (N <= 3) {
-    ngram_rows<N, FT, KM, ROWS>(sim, a, F, feat, qterm, col0, warp * ROWS, lane);
+    ngram_rows<N, FT, KM, ROWS>(sim, a, F, feat, qterm, col0, warp * ROWS, lane, ncols, merge);
   } else {
-    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS, lane);
-    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS + ROWS / 2, lane);
+    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS, lane, ncols, merge);
+    ngram_rows<N, FT, KM, ROWS / 2>(sim, a, F, feat, qterm, col0, warp * ROWS + ROWS / 2, lane, ncols, merge);
   }
 }
 
 template <int FT, int KM>
-__device__ __forceinline__ void ngram_dispatch_n(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane) {
+__device__ __forceinline__ void ngram_dispatch_n(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane, int ncols,
+                                                 bool merge) {
   switch (n) {
-    case 1: ngram_pass<1, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 2: ngram_pass<2, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 3: ngram_pass<3, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    case 4: ngram_pass<4, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
-    default: ngram_pass<5, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane); break;
+    case 1: ngram_pass<1, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane, ncols, merge); break;
+    case 2: ngram_pass<2, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane, ncols, merge); break;
+    case 3: ngram_pass<3, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane, ncols, merge); break;
+    case 4: ngram_pass<4, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane, ncols, merge); break;
+    default: ngram_pass<5, FT, KM>(s, a, a.F, feat, qterm, col0, warp, lane, ncols, merge); break;
   }
 }
 
 template <int FT>
-__device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane) {
-  if (a.kmax <= 2) ngram_dispatch_n<FT, 2>(n, s, a, feat, qterm, col0, warp, lane);  // the reference default (kmax = 2)
-  else ngram_dispatch_n<FT, MAX_KMAX>(n, s, a, feat, qterm, col0, warp, lane);
+__device__ __forceinline__ void ngram_dispatch(int n, const float* s, const PacrrArgs& a, float* feat, int qterm, int col0, int warp, int lane, int ncols,
+                                               bool merge) {
+  if (a.kmax <= 2) ngram_dispatch_n<FT, 2>(n, s, a, feat, qterm, col0, warp, lane, ncols, merge);  // the reference default (kmax = 2)
+  else ngram_dispatch_n<FT, MAX_KMAX>(n, s, a, feat, qterm, col0, warp, lane, ncols, merge);
 }
 
 template <class Sync>
@@ -171,17 +190,22 @@ __device__ __forceinline__ void pacrr_tail(const PacrrArgs& a, int pair, float* 
 
 // Everything after the cosine tile: n-gram conv/max/top-k passes, softmax(idf) channel, 3-layer combine MLP.
 // Runs on 8 warps (tid 0..255); `sync` is the barrier of exactly those warps.
-template <class Sync>
-__device__ __forceinline__ void pacrr_epilogue(const float* sim, const PacrrArgs& a, int pair, float* feat, float* h1, float* h2, int tid,
-                                               Sync sync) {
+// The n-gram conv / max / top-k passes over one doc tile of `ncols` eligible positions (8 warps, tid 0..255).
+__device__ __forceinline__ void pacrr_convs(const float* sim, const PacrrArgs& a, float* feat, int tid, int ncols, bool merge) {
   const int lane = tid & 31, warp = tid >> 5;
   const int ngrams = a.maxgram - a.mingram + 1;
   const int qterm = ngrams * a.kmax + (a.idf ? 1 : 0);
   for (int g = 0; g < ngrams; ++g) {
     const int n = a.mingram + g;
-    if (a.F == 32) ngram_dispatch<32>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
-    else ngram_dispatch<0>(n, sim, a, feat, qterm, g * a.kmax, warp, lane);
+    if (a.F == 32) ngram_dispatch<32>(n, sim, a, feat, qterm, g * a.kmax, warp, lane, ncols, merge);
+    else ngram_dispatch<0>(n, sim, a, feat, qterm, g * a.kmax, warp, lane, ncols, merge);
   }
+}
+
+template <class Sync>
+__device__ __forceinline__ void pacrr_epilogue(const float* sim, const PacrrArgs& a, int pair, float* feat, float* h1, float* h2, int tid,
+                                               Sync sync) {
+  pacrr_convs(sim, a, feat, tid, a.D, false);
   pacrr_tail(a, pair, feat, h1, h2, tid, sync);
 }
 
@@ -243,9 +267,20 @@ __global__ void __launch_bounds__(NT, 1) pacrr_kernel(const PacrrArgs a) {
   float* h2 = h1 + MAX_COMBINE;                                                // [MAX_COMBINE]
   clear_sim_tile(s, tid);
   __syncthreads();
+  // Doc tiling (maxdoclen > 512; the reference extractor's default is 800): tiles of 512 columns start every S = 512 - (maxgram - 1)
+  // columns, so that every conv window that starts in [0, S) of a tile lies inside it; only those positions are eligible for the
+  // tile's top-k (the last tile: all of its columns -- there the zero padding past the document is the reference's own,
+  // PACRR.py:64), and the per-row top-k lists are carried from tile to tile in `feat`.
+  const int S = DT - (a.maxgram - 1);
+  const int tiles = a.D <= DT ? 1 : 1 + (a.D - DT + S - 1) / S;
   for (int pair = blockIdx.x; pair < a.B; pair += gridDim.x) {
-    build_sim_tile(s, a.table, a.pitch, a.V, a.q + (size_t)pair * a.Q, a.Q, a.d + (size_t)pair * a.D, 0, a.D, true, tid);
-    pacrr_epilogue(s.sim, a, pair, feat, h1, h2, tid, BlockSync());
+    for (int t = 0; t < tiles; ++t) {
+      const int d0 = t * S;
+      build_sim_tile(s, a.table, a.pitch, a.V, a.q + (size_t)pair * a.Q, a.Q, a.d + (size_t)pair * a.D, d0, a.D, t == 0, tid);
+      pacrr_convs(s.sim, a, feat, tid, t + 1 < tiles ? S : a.D - d0, t > 0);
+      __syncthreads();  // the tile is rebuilt / `feat` is read by the tail
+    }
+    pacrr_tail(a, pair, feat, h1, h2, tid, BlockSync());
   }
 }
 
@@ -521,7 +556,8 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   CAPR_REQUIRE(B == 0 || (query && doc && table && (!tc_engine || table_lo) && conv_w && conv_b && l1w && l1b && l2w && l2b && l3w && l3b && scores), CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
   CAPR_REQUIRE(((uintptr_t)table & 15) == 0, CAPR_ERR_BAD_POINTER, "%s: table must be 16-byte aligned", fn);
   CAPR_REQUIRE(Q <= QT, CAPR_ERR_UNSUPPORTED, "%s: maxqlen=%d > %d is not supported by the fused kernels yet", fn, Q, QT);
-  CAPR_REQUIRE(D <= DT, CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d is not supported by the PACRR kernel yet", fn, D, DT);
+  CAPR_REQUIRE(D <= (tc_engine ? DT : 8 * DT), CAPR_ERR_UNSUPPORTED, "%s: maxdoclen=%d > %d is not supported by this engine%s", fn, D, tc_engine ? DT : 8 * DT,
+               tc_engine ? " (capr_pacrr_forward tiles the document)" : "");
   CAPR_REQUIRE(D >= kmax, CAPR_ERR_BAD_SHAPE, "%s: kmax=%d exceeds maxdoclen=%d", fn, kmax, D);
   CAPR_REQUIRE(pitch <= (tc_engine ? simtc::MAX_ATOMS * simtc::ATOM_K : MAX_PITCH), CAPR_ERR_UNSUPPORTED, "%s: embedding dim > %d is not supported by this engine", fn, tc_engine ? simtc::MAX_ATOMS * simtc::ATOM_K : MAX_PITCH);
   CAPR_REQUIRE(maxgram <= MAX_NGRAM && maxgram - mingram + 1 <= MAX_GRAMS, CAPR_ERR_UNSUPPORTED, "%s: maxgram=%d > %d is not supported", fn, maxgram, MAX_NGRAM);

@@ -90,8 +90,11 @@ class ConvKNRM_class(nn.Module):
 
     def _run(self, sentence, query_sentence, want_feats=False):
         _lib.require_cuda(sentence, query_sentence)
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
-            raise NotImplementedError("capreolus_b200 ConvKNRM: only inference (torch.no_grad / requires_grad=False) is implemented")
+        if self.training and torch.is_grad_enabled() and not want_feats and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
+            # training: the Conv1d encoders sit upstream of the cosine, so the whole forward is the torch restatement (train_heads.py)
+            from capreolus_b200.reranker import train_heads
+
+            return train_heads.convknrm_forward(self, sentence, query_sentence), None
         q, d = _ids(query_sentence), _ids(sentence)
         B, Q = q.shape
         D = d.shape[1]

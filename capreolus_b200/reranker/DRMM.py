@@ -49,8 +49,13 @@ class DRMM_class(nn.Module):
 
     def _run(self, sentence, query_sentence, query_idf, want_hist=False):
         _lib.require_cuda(sentence, query_sentence, query_idf)
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
-            raise NotImplementedError("capreolus_b200 DRMM: only inference (torch.no_grad / requires_grad=False) is implemented")
+        if self.training and torch.is_grad_enabled() and not want_hist and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
+            # training: histogram from the CUDA engine (frozen embedding, no gradient needed), parameterised tail in torch (train_heads.py)
+            from capreolus_b200.reranker import train_heads
+
+            with torch.no_grad():
+                hist = self._run(sentence, query_sentence, query_idf, want_hist=True)[1]
+            return train_heads.drmm_forward(self, hist, _ids(query_sentence), query_idf), None
         q, d = _ids(query_sentence), _ids(sentence)
         B, Q = q.shape
         D = d.shape[1]

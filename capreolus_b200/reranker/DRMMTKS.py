@@ -40,8 +40,15 @@ class DRMMTKS_class(nn.Module):
             # DRMMTKS.py:59 hands the int64 token ids to _term_gate, whose TV branch applies Linear(E,1) to them (l.43):
             # the reference raises there, so there is no behaviour to reproduce
             raise ValueError("Invalid value for gateType: DRMMTKS supports gateType='IDF' only (the reference's 'TV' branch cannot run)")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
-            raise NotImplementedError("capreolus_b200 DRMMTKS: only inference (torch.no_grad / requires_grad=False) is implemented")
+        if self.training and torch.is_grad_enabled() and not want_topk and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
+            # training: top-k cosines from the CUDA engine, parameterised tail in torch (train_heads.py)
+            from capreolus_b200.reranker import train_heads
+
+            if self.embedding.weight.requires_grad:
+                raise NotImplementedError("capreolus_b200 DRMMTKS: freezeemb=False (gradient to the embedding table) is not implemented")
+            with torch.no_grad():
+                topk = self._run(doc, query, query_idf, want_topk=True)[1]
+            return train_heads.drmmtks_forward(self, topk, _ids(query), query_idf), None
         q, d = _ids(query), _ids(doc)
         B, Q = q.shape
         D = d.shape[1]

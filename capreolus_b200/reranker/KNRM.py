@@ -81,7 +81,12 @@ class KNRM_class(nn.Module):
         needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())  # eval mode: inference kernel
         if needs_grad:
             if self.embedding.weight.requires_grad:
-                raise NotImplementedError("capreolus_b200 KNRM: finetune=True (gradient to the embedding table) is not implemented")
+                # finetune=True (KNRM.py:23-24,68): the gradient reaches the embedding table, which the fused kernels treat as
+                # frozen -> torch restatement of the forward on the device (train_heads.py); the prepared tables are rebuilt from
+                # the updated weight at the next inference call (PreparedTable keys on the weight's version counter)
+                from capreolus_b200.reranker import train_heads
+
+                return train_heads.knrm_forward(self, doctoks, querytoks)
             return self.combine(self.kernel_features(doctoks, querytoks))
         q, d = _ids(querytoks), _ids(doctoks)
         B, Q = q.shape

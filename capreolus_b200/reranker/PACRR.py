@@ -53,8 +53,13 @@ class PACRR_class(nn.Module):
 
     def _run(self, sentence, query_sentence, query_idf, want_topk=False):
         _lib.require_cuda(sentence, query_sentence)
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
-            raise NotImplementedError("capreolus_b200 PACRR: only inference (torch.no_grad / requires_grad=False) is implemented")
+        if self.training and torch.is_grad_enabled() and not want_topk and any(p.requires_grad for p in self.parameters()):  # eval mode scores with the inference kernels whatever the grad mode
+            # training: cosine matrix from the CUDA engine (capr_simmat_forward), Conv2d / max / top-k / MLP in torch (train_heads.py)
+            from capreolus_b200.reranker import train_heads
+
+            with torch.no_grad():
+                sim = self.simmat(query_sentence, sentence)
+            return train_heads.pacrr_forward(self, sim, query_idf), None
         p = self.p
         q, d = _ids(query_sentence), _ids(sentence)
         B, Q = q.shape

@@ -271,6 +271,37 @@ def test_pacrr_fresh_shapes(B, Q, D, V, E, engine):
     assert rel_err(got, want) < TOL
 
 
+@pytest.mark.parametrize("B,Q,D,V,E", [(3, 32, 800, 3000, 300), (2, 20, 1023, 1000, 100), (2, 8, 513, 500, 64), (2, 32, 1530, 2000, 300)])
+def test_pacrr_long_documents_are_tiled(B, Q, D, V, E):
+    """maxdoclen > 512 (the reference EmbedText extractor's default is 800): capr_pacrr_forward tiles the document, carrying the
+    per-row top-k lists from tile to tile -- scores and the top-k features themselves against the oracle."""
+    from capreolus_b200 import reranker as R, synthetic
+    from oracle import restated
+
+    got, want = _fresh("PACRR", "pacrr_forward", PACRR_CFG["default"], B, Q, D, V, E, seed=61)
+    assert rel_err(got, want) < TOL
+    table = synthetic.embedding_table(V, E, seed=61)
+    batch = {k: torch.from_numpy(v) for k, v in synthetic.parity_batch(B, Q, D, V, seed=62, oov=True).items()}
+    torch.manual_seed(61)
+    rr = R.PACRR(PACRR_CFG["default"], provide={"extractor": Extractor(table, Q, D)})
+    model = rr.build_model().eval()
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sim = restated.similarity_matrix(torch.from_numpy(table), batch["query"], batch["posdoc"])
+    want_topk = torch.cat([restated.pacrr_ngram_topk(sim, state[f"ngrams.{i}.conv.weight"], state[f"ngrams.{i}.conv.bias"], n, 2)
+                           for i, n in enumerate(range(1, 4))], dim=2).numpy()
+    model.to(DEV)
+    with torch.no_grad():
+        got_topk = model.ngram_topk(batch["posdoc"].to(DEV), batch["query"].to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(got_topk, want_topk, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("cls,fn,cfg", [("ConvKNRM", "convknrm_forward", {}), ("KNRM", "knrm_forward", {}), ("DRMMTKS", "drmmtks_forward", {})])
+def test_default_extractor_doclen_800(cls, fn, cfg):
+    """The reference extractor's default maxdoclen = 800 runs on the tensor-core engines of the other models too."""
+    got, want = _fresh(cls, fn, cfg, 4, 32, 800, 3000, 300, seed=71, oov=cls != "ConvKNRM")
+    assert rel_err(got, want) < TOL
+
+
 def test_errors_and_edge_cases():
     from capreolus_b200 import reranker as R, synthetic
 

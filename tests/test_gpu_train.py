@@ -155,3 +155,104 @@ def test_knrm_loss_curve_matches_reference_trainer(shape, dims, setting):
         json.dump({"golden": f"tests/golden/knrm_train.npz::{shape_name}", "losses": losses, "reference_losses": [float(x) for x in g[f"{shape_name}/losses"]],
                    "loss_rel_err": [float(abs(a - b) / abs(b)) for a, b in zip(losses, g[f"{shape_name}/losses"])], "params_within_bar": [close, total],
                    "skipped": list(skip), "max_abs_param_deviation": worst}, f, indent=1)
+
+
+# ---- training of the other embedding-id rerankers (round 2): CUDA engine upstream of the parameters + torch tail -------------
+def _train_case(name, cfg, Q=8, D=40, V=500, E=50, B=6, seed=3):
+    from capreolus_b200 import reranker as R, synthetic
+
+    table = synthetic.embedding_table(V, E, seed=seed)
+    rr = getattr(R, name)(cfg, provide={"extractor": Extractor(table, Q, D)})
+    torch.manual_seed(7)
+    model = rr.build_model()
+    batch = synthetic.train_triples(B, Q, D, V, seed=seed + 1, disjoint=True)
+    cpu = {k: torch.from_numpy(v) for k, v in batch.items()}
+    return rr, model, table, cpu
+
+
+@pytest.mark.parametrize("name,oracle_fn,cfg", [
+    ("DRMM", "drmm_forward", {}),
+    ("DRMMTKS", "drmmtks_forward", {}),
+    ("PACRR", "pacrr_forward", {}),
+    ("ConvKNRM", "convknrm_forward", {}),
+])
+def test_other_rerankers_train_through_the_drop_in(name, oracle_fn, cfg):
+    """``reranker.score(batch)`` in train mode is differentiable for every embedding-id reranker: loss and parameter gradients agree
+    with autograd through the CPU oracle (the reference's op sequence), and one Adam step of ``PairwiseTrainer`` runs."""
+    from capreolus_b200.reranker.common import pair_hinge_loss
+    from capreolus_b200.trainer import PairwiseTrainer
+    from oracle import restated
+
+    rr, model, table, cpu = _train_case(name, cfg)
+    with torch.no_grad():  # untrained scores can sit far from the hinge: scale the last layer so that pairs are active
+        last = [m for m in model.modules() if isinstance(m, torch.nn.Linear)][-1]
+        last.weight.mul_(0.05)
+    state = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "embedding" not in k) for k, v in model.state_dict().items()}
+    ttable = torch.from_numpy(table)
+    fn = getattr(restated, oracle_fn)
+    pos = fn(state, ttable, cpu["posdoc"], cpu["query"], cpu["query_idf"]).view(-1)
+    neg = fn(state, ttable, cpu["negdoc"], cpu["query"], cpu["query_idf"]).view(-1)
+    loss_ref = restated.pair_hinge_loss(pos, neg)
+    loss_ref.backward()
+    model.to(DEV).train()
+    gpu = {k: v.to(DEV) for k, v in cpu.items()}
+    loss = pair_hinge_loss(rr.score(gpu))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=2e-4, atol=1e-6)
+    checked = 0
+    # gradients that are sums of many cancelling terms (e.g. d/dmu of a kernel far from the cosines) are small next to the others and
+    # carry the fp32 summation-order noise of BOTH sides: the absolute floor is 1e-4 of the largest gradient of the model
+    gscale = max(float(v.grad.abs().max()) for v in state.values() if v.grad is not None)
+    for pname, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        want = state[pname].grad
+        if want is None:
+            continue
+        assert p.grad is not None, pname
+        scale = max(float(want.abs().max()), 1e-6)
+        assert float((p.grad.cpu() - want).abs().max()) <= 5e-3 * scale + 1e-4 * gscale + 1e-6, (pname, p.grad.cpu().flatten()[:6], want.flatten()[:6])
+        checked += 1
+    assert checked >= 3
+    # eval mode still goes through the inference kernels and agrees with the training path's forward
+    model.eval()
+    with torch.no_grad():
+        ev = rr.score(gpu)[0]
+    model.train()
+    tr = rr.score(gpu)[0]
+    np.testing.assert_allclose(ev.cpu().numpy(), tr.detach().cpu().numpy(), rtol=1e-3, atol=1e-4)
+    trainer = PairwiseTrainer(batch=3, itersize=6, lr=1e-3, device=DEV)
+    trainer.prepare(rr)
+    before = {k: v.detach().clone() for k, v in model.named_parameters() if v.requires_grad}
+    trainer.single_train_iteration(rr, iter([{k: v[:3] for k, v in cpu.items()}, {k: v[3:] for k, v in cpu.items()}]))
+    assert any(not torch.equal(before[k], v.detach()) for k, v in model.named_parameters() if v.requires_grad)
+
+
+def test_knrm_finetune_trains_the_embedding_table():
+    """KNRM ``finetune=True`` (KNRM.py:23-24,68): the gradient reaches ``embedding.weight``; loss and table gradient agree with
+    autograd through the oracle, and the next inference call sees the updated table (PreparedTable is rebuilt)."""
+    from capreolus_b200.reranker.common import pair_hinge_loss
+    from oracle import restated
+
+    rr, model, table, cpu = _train_case("KNRM", {"finetune": True})
+    with torch.no_grad():
+        model.combine[0].weight.mul_(0.02)
+    assert model.embedding.weight.requires_grad
+    state = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    pos = restated.knrm_forward(state, state["embedding.weight"], cpu["posdoc"], cpu["query"]).view(-1)
+    neg = restated.knrm_forward(state, state["embedding.weight"], cpu["negdoc"], cpu["query"]).view(-1)
+    loss_ref = restated.pair_hinge_loss(pos, neg)
+    loss_ref.backward()
+    model.to(DEV).train()
+    gpu = {k: v.to(DEV) for k, v in cpu.items()}
+    loss = pair_hinge_loss(rr.score(gpu))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=2e-4)
+    g, want = model.embedding.weight.grad.cpu(), state["embedding.weight"].grad
+    assert float((g - want).abs().max()) <= 5e-3 * float(want.abs().max()) + 1e-7
+    model.eval()
+    with torch.no_grad():
+        s0 = rr.test(gpu).clone()
+        model.embedding.weight.add_(-0.5 * model.embedding.weight.grad)  # an (exaggerated) optimizer step on the table
+        s1 = rr.test(gpu)
+    assert not torch.allclose(s0, s1)
