@@ -357,6 +357,7 @@ struct Model {
   bool attention_v2 = false;    // CAPR_BERT_ATTENTION=v2: one CTA per (sequence, head, 256 queries) instead of the persistent kernel
   bool gemm_pairs = true;       // CAPR_BERT_GEMM=1cta: force the one-CTA GEMM (A/B tests)
   int max_pairs = 0;            // co-resident CTA pairs of gemm2_kernel (cudaOccupancyMaxActiveClusters)
+  int qk_products = 3;          // bf16 products of S = Q.K^T in attention_tc4_kernel (CAPR_BERT_QK_PRODUCTS=1|2|3, see bert_attn2.cuh)
 };
 
 static int dev_alloc(Model* m, void** p, size_t bytes) {
@@ -534,6 +535,8 @@ int capr_bert_create(const capr_bert_config* cfg, const float* const* weights, i
     m->attention_v2 = e && e[0] == 'v' && e[1] == '2';
     const char* ge = getenv("CAPR_BERT_GEMM");
     m->gemm_pairs = !(ge && ge[0] == '1');
+    const char* qe = getenv("CAPR_BERT_QK_PRODUCTS");
+    m->qk_products = (qe && qe[0] >= '1' && qe[0] <= '3') ? qe[0] - '0' : 3;
   }
   const size_t H = cfg->hidden, I = cfg->intermediate;
   int rc = CAPR_OK;
@@ -685,7 +688,7 @@ static int bert_run(const char* fn, capr_bert_t h, const int64_t* ids, const int
   const char* atr = nullptr;
 #endif
   const Attn2Args at2{L, H, heads, n_seq, (long long)Tp, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo, adbg ? atoi(adbg) : 0,
-                      atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr, 0};
+                      atr ? (long long*)strtoull(atr, nullptr, 10) : nullptr, m->qk_products, 0};
   const int att_tc2_grid = n_seq * heads * ((L + A2_BLOCKS * AT_BQ - 1) / (A2_BLOCKS * AT_BQ));
   const AttnArgs at{L, H, heads, n_seq, scale_log2e, (const long long*)mask, ws.ctx_hi, ws.ctx_lo};
   const int att_tc_grid = n_seq * heads * ((L + AT_BQ - 1) / AT_BQ);

@@ -41,6 +41,10 @@ struct Attn2Args {
   __nv_bfloat16* ctx_lo;
   int debug;              // profiling only (CAPR_ATTN_DEBUG; results invalid): 1 no softmax math, 2 no P.V MMAs, 4 no K/V reloads, 8 no Q.K MMAs
   long long* trace;       // profiling only (CAPR_ATTN_TRACE): CTA 0 of the grid records clock64 stamps, [role][event] (see TR_* below)
+  int qk_products;        // attention_tc4_kernel only: bf16 products of S = Q.K^T: 3 = q_hi.k_hi + q_lo.k_hi + q_hi.k_lo (round 1), 2 = without
+                          // q_hi.k_lo, 1 = q_hi.k_hi alone.  The scores only feed a softmax: scripts/bert_precision_probe2.py measures the
+                          // final score error of BERT-base at 2.8e-5 (3), 1.4e-4 (2), 2.3e-4 (1) against the 1e-3 bar; every Linear layer
+                          // and P.V need all three products (dropping one costs >= 6.7e-4).
   int q_blocks;           // attention_tc4_kernel only: 256-query blocks per (sequence, head) to compute, 0 = all of them.  The last
                           // encoder layer of a classification forward needs the [CLS] row alone (ptBERTMaxP.py:82 reads logits of
                           // the pooled row 0), i.e. block 0.

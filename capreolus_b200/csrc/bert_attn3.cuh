@@ -181,8 +181,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_c
           for (int k = 0; k < AT_DH / 16; ++k) {
             const uint32_t ko = k * 32;
             tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, k != 0);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
-            tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_lo + ko), idesc_qk, true);
+            if (a.qk_products >= 2) tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_lo + ko), tc::make_sw128_kmajor_desc(k_hi + ko), idesc_qk, true);
+            if (a.qk_products >= 3) tc::umma_f16(d_tmem, tc::make_sw128_kmajor_desc(q_hi + ko), tc::make_sw128_kmajor_desc(k_lo + ko), idesc_qk, true);
           }
           tc::umma_commit(&s_full[g * 2 + buf]);
           if (g == A2_BLOCKS - 1 && t == n - 1) tc::umma_commit(q_empty);  // the item's last Q.K^T: the Q tiles may be replaced

@@ -316,9 +316,9 @@ int capr_knrm_forward_tf(const int64_t* query, const int64_t* doc, int B, int Q,
   const int red_floats = simtc3::POOL_WARPS * (KT + 1) * 32;
   // two query buffers (no bubble while the next pair's query block is gathered) or one (three more stages in flight)
   const char* qb_env = getenv("CAPR_SIM3_QBUFS");
-  int n_qbufs = (qb_env && qb_env[0] == '1') ? 1 : 2;
+  int n_qbufs = (qb_env && qb_env[0] == '2') ? 2 : 1;
   int n_stages = simtc3::stages_that_fit(atoms, n_qbufs, dcap, red_floats);
-  if (n_stages < 4 && n_qbufs == 2) n_qbufs = 1, n_stages = simtc3::stages_that_fit(atoms, 1, dcap, red_floats);
+  if (n_stages < 2 && n_qbufs == 2) n_qbufs = 1, n_stages = simtc3::stages_that_fit(atoms, 1, dcap, red_floats);
   CAPR_REQUIRE(n_stages >= 2, CAPR_ERR_UNSUPPORTED, "%s: shared-memory budget exceeded (D=%d, pitch=%d)", fn, D, pitch);
   if (const char* st_env = getenv("CAPR_SIM3_STAGES")) {
     const int want = atoi(st_env);

@@ -20,8 +20,8 @@
 //     accumulated into the SAME accumulator rows (3 MMAs per K step, N <= 128), so a TMEM lane holds finished cosines and the
 //     pooling warps of quarter q read them with tcgen05.ld.32x32b (lane = query row) -- no drain warps, no staging tile, and
 //     four 128-column accumulators decouple MMA from pooling four units deep.
-//  3. A DEEPER RING.  The 74 KB tile and the drain hand-offs are gone: 16 KB stages (128 doc rows x one 64-element K atom of
-//     one plane), 7 stages + two query buffers or 10 stages + one (CAPR_SIM3_QBUFS), i.e. 112-160 KB of gathers in flight.
+//  3. A DEEPER RING.  The 74 KB tile and the drain hand-offs are gone: 32 KB stages (128 doc rows x one 64-element K atom, hi and
+//     lo planes), 5 stages with one query buffer (default) or 3 with two (CAPR_SIM3_QBUFS=2), i.e. up to 160 KB of gathers in flight.
 //
 // Work unit = (pair, 128 distinct doc tokens).  Roles (14 warps): 0-7 pooling (quarter = warp % 4, column half = warp / 4),
 // 8-11 gather producers, 12 MMA issuer + TMEM owner, 13 finisher (cross-warp reduction, log, combine).
@@ -40,14 +40,17 @@ constexpr int FIN_WARP = MMA_WARP + 1;                       // 13
 constexpr int ATOM_K = 64;                                   // bf16 elements per 128-byte swizzle row
 constexpr int MAX_ATOMS = 5;                                 // pitch <= 320
 constexpr int U_DOCS = 128;                                  // distinct doc tokens per work unit (= max MMA N)
-constexpr int STAGE_BYTES = U_DOCS * 128;                    // one plane of 128 rows x one K atom = 16 KB
+constexpr int PLANE_BYTES = U_DOCS * 128;                    // one plane of 128 rows x one K atom = 16 KB
+constexpr int STAGE_BYTES = 2 * PLANE_BYTES;                 // a stage = hi plane + lo plane of one K atom = 32 KB: the hand-off of a stage costs
+                                                             // ~450-700 cycles whatever its size (producer arrive -> MMA wait -> commit -> producer
+                                                             // wait; all-off ablation), so a unit is 5 hand-offs instead of 10
 constexpr int Q_ATOM_BYTES = 64 * 128;                       // per K atom: rows 0-31 = q_hi, rows 32-63 = q_lo
 constexpr int Q_PLANE_BYTES = 32 * 128;                      // 4 KB: the A descriptor of quarter q starts q * 4 KB before the tile
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 6;
 constexpr int MAX_DCAP = 1024;                               // maxdoclen <= 1024
 constexpr int IDS_PER_THREAD = MAX_DCAP / PROD_THREADS;      // 8
 constexpr size_t MAX_DYN_SMEM = 232448;                      // 227 KB
-constexpr int N_BARS = 2 + 2 + 2 * MAX_STAGES + 4 + 4 + 2 + 2 + 2;  // 42
+constexpr int N_BARS = 2 + 2 + 2 * MAX_STAGES + 4 + 4 + 2 + 2 + 2;
 
 struct Problem {
   const long long* q;          // [B,Q] raw query ids (int64, reference layout)
@@ -270,11 +273,11 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
         live |= (trow != 0 ? 1u : 0u) << j;
       }
       for (int a = 0; a < atoms; ++a) {
+        tc::mbar_wait(&s.d_empty[stage], d_phase ^ 1);
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
-          tc::mbar_wait(&s.d_empty[stage], d_phase ^ 1);
-          const uint32_t base = tc::smem_u32(s.stage(stage));
+          const uint32_t base = tc::smem_u32(s.stage(stage)) + plane * PLANE_BYTES;
           if (a + 1 < atoms || sub < last_chunks) {  // tail chunks of a partial last atom are never read
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -285,9 +288,9 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
                              : "memory");
             }
           }
-          cp_async_arrive_noinc(&s.d_full[stage]);
-          if (++stage == pr.n_stages) stage = 0, d_phase ^= 1;
         }
+        cp_async_arrive_noinc(&s.d_full[stage]);
+        if (++stage == pr.n_stages) stage = 0, d_phase ^= 1;
       }
     }
     SIM3_TR(0, 7);
@@ -330,32 +333,19 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
         const uint64_t a_hi = tc::make_sw128_kmajor_desc(a_base + a * Q_ATOM_BYTES);
         const uint64_t a_lo = tc::make_sw128_kmajor_desc(a_base + a * Q_ATOM_BYTES + Q_PLANE_BYTES);
         const int ksteps = CAPR_DBG(pr.debug & 2) ? 0 : min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
-        // d_hi stage: q_hi.d_hi and q_lo.d_hi
+        // one stage = d_hi and d_lo of this K atom: q_hi.d_hi + q_lo.d_hi + q_hi.d_lo
         tc::mbar_wait(&s.d_full[stage], d_phase);
         if (a == 0) SIM3_TR(1, 14);
         tc::tc_fence_after();
         {
-          const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.stage(stage)));
+          const uint64_t bd_hi = tc::make_sw128_kmajor_desc(tc::smem_u32(s.stage(stage)));
+          const uint64_t bd_lo = tc::make_sw128_kmajor_desc(tc::smem_u32(s.stage(stage)) + PLANE_BYTES);
           if (tc::elect_one()) {
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per K=16 step, in 16-byte units
-              tc::umma_f16(d_tmem, a_hi + koff, bd + koff, idesc, (a | k) != 0);
-              tc::umma_f16(d_tmem, a_lo + koff, bd + koff, idesc, true);
-            }
-            tc::umma_commit(&s.d_empty[stage]);
-          }
-          __syncwarp();
-          if (++stage == pr.n_stages) stage = 0, d_phase ^= 1;
-        }
-        // d_lo stage: q_hi.d_lo
-        tc::mbar_wait(&s.d_full[stage], d_phase);
-        tc::tc_fence_after();
-        {
-          const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.stage(stage)));
-          if (tc::elect_one()) {
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t koff = (uint64_t)(k * 2);
-              tc::umma_f16(d_tmem, a_hi + koff, bd + koff, idesc, true);
+              tc::umma_f16(d_tmem, a_hi + koff, bd_hi + koff, idesc, (a | k) != 0);
+              tc::umma_f16(d_tmem, a_lo + koff, bd_hi + koff, idesc, true);
+              tc::umma_f16(d_tmem, a_hi + koff, bd_lo + koff, idesc, true);
             }
             tc::umma_commit(&s.d_empty[stage]);
           }

@@ -105,7 +105,7 @@ def test_engine3_matches_oracle_identity_prepass_and_engine2(B, Q, D, V, E, monk
         monkeypatch.setenv("CAPR_KNRM_TF", "0")  # identity pre-pass: every position its own token
         ident = rr.test(gpu).cpu().numpy()
         monkeypatch.delenv("CAPR_KNRM_TF")
-        monkeypatch.setenv("CAPR_SIM3_QBUFS", "1")  # the other shared-memory layout: one query buffer, a deeper ring
+        monkeypatch.setenv("CAPR_SIM3_QBUFS", "2")  # the other shared-memory layout: two query buffers, a shorter ring
         one_q = rr.test(gpu).cpu().numpy()
         monkeypatch.delenv("CAPR_SIM3_QBUFS")
         monkeypatch.setattr(common, "ENGINE", "tc")
