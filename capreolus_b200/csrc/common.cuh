@@ -66,6 +66,16 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(live ? 16u : 0u) : "memory");
 }
+// Predicated 16-byte copy (PTX predicate, no branch: a C++ `if` around the asm statement makes ptxas emit a divergent branch per
+// copy, which halved the producer's issue rate -- round-2 A/B) with src-size `nbytes` (0 = zero-fill without a global read).
+__device__ __forceinline__ void cp_async16_pred(uint32_t smem_dst, const void* gmem_src, uint32_t nbytes, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}\n" ::"r"(smem_dst),
+      "l"(gmem_src), "r"(nbytes), "r"((uint32_t)pred)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

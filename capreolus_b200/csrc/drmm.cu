@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
   int* cnt = reinterpret_cast<int*>(spare);                          // atomic mode: [QT][CNT_PITCH_TC]
   float* ub = PRIV ? reinterpret_cast<float*>(spare + HIST_WARPS_IN_SPARE * HIST_WARP_B) : reinterpret_cast<float*>(cnt + QT * CNT_PITCH_TC);  // [MAX_SLOTS_TC]
   float* z = ub + MAX_SLOTS_TC;                                      // [QT]
-  const uint32_t tmem_base = setup(s, tid, (int)blockDim.x, MMA_WARP_PIPE, a.pr.group_arrive, a.pr.prod_warps);
-  if (is_producer_warp(warp, a.pr.prod_warps)) {
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
+  if (is_producer_warp(warp)) {
     producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
   } else if (warp == MMA_WARP_PIPE) {
     mma_loop(s, a.pr, tmem_base);
@@ -380,9 +380,6 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
   const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
   a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
-  a.pr.group_arrive = simtc::group_arrive_default();
-  a.pr.prod_warps = 4;  // (8 producer warps: KNRM only so far, knrm_tc.cu)
-  const int n_threads = simtc::THREADS_PIPE;
   const size_t smem = simtc::smem_bytes(atoms, DRMM_TC_EXTRA_BYTES, a.pr.deep != 0);
   CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: %zu bytes of shared memory needed", fn, smem);
   // CAPR_DRMM_POOL = atomic | noadd | skip selects the A/B reference and the profiling-only ablations (results invalid for the last two)
@@ -394,7 +391,7 @@ extern "C" int capr_drmm_forward_tc(const int64_t* query, const int64_t* doc, co
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, n_threads, smem, (cudaStream_t)stream>>>(a);
+    kernel<<<grid, simtc::THREADS_PIPE, smem, (cudaStream_t)stream>>>(a);
     return cudaSuccess;
   };
   switch (a.pool_mode) {

@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmmtks_tc_kernel(cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
   float* z = spare_scratch(s);  // [QT] ffw output per query term
-  const uint32_t tmem_base = setup(s, tid, (int)blockDim.x, MMA_WARP_PIPE, a.pr.group_arrive, a.pr.prod_warps);
-  if (is_producer_warp(warp, a.pr.prod_warps)) {
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
+  if (is_producer_warp(warp)) {
     producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
   } else if (warp == MMA_WARP_PIPE) {
     mma_loop(s, a.pr, tmem_base);
@@ -171,9 +171,6 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
   const int atoms = (pitch + simtc::ATOM_K - 1) / simtc::ATOM_K;
   const char* ring_env = getenv("CAPR_SIM_RING");  // see capr_knrm_forward_tc
   a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
-  a.pr.group_arrive = simtc::group_arrive_default();
-  a.pr.prod_warps = 4;  // (8 producer warps: KNRM only so far, knrm_tc.cu)
-  const int n_threads = simtc::THREADS_PIPE;
   const size_t smem = simtc::smem_bytes(atoms, 0, a.pr.deep != 0);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
@@ -181,10 +178,10 @@ extern "C" int capr_drmmtks_forward_tc(const int64_t* query, const int64_t* doc,
   cudaStream_t st = (cudaStream_t)stream;
   if (topk <= 10) {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmmtks_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    drmmtks_tc_kernel<10><<<grid, n_threads, smem, st>>>(a);
+    drmmtks_tc_kernel<10><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   } else {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(drmmtks_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    drmmtks_tc_kernel<32><<<grid, n_threads, smem, st>>>(a);
+    drmmtks_tc_kernel<32><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

@@ -22,18 +22,16 @@ struct KnrmTcArgs {
   float* feats;
 };
 
-// P8: the launch with 8 producer warps (672 threads, 96-register cap) is a separate instantiation so that the default
-// (4 producer warps, 544 threads) keeps its register allocation.
-template <int KT, bool P8 = false>
-__global__ void __launch_bounds__(P8 ? simtc::THREADS_PIPE_MAX : simtc::THREADS_PIPE, 1) knrm_tc_kernel(const KnrmTcArgs a) {
+template <int KT>
+__global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const KnrmTcArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem s = carve(smem_raw, (a.pr.pitch + ATOM_K - 1) / ATOM_K, a.pr.deep != 0);
   float* sPart = s.extra;  // [2][POOL_WARPS][KT] per-warp partial features, double-buffered by pair parity
-  const uint32_t tmem_base = setup(s, tid, (int)blockDim.x, MMA_WARP_PIPE, a.pr.group_arrive, a.pr.prod_warps);
+  const uint32_t tmem_base = setup(s, tid, THREADS_PIPE, MMA_WARP_PIPE);
 
-  if (is_producer_warp(warp, a.pr.prod_warps)) {
+  if (is_producer_warp(warp)) {
     producer_loop(s, a.pr, producer_index(warp) * 32 + lane);
   } else if (warp == MMA_WARP_PIPE) {
     mma_loop(s, a.pr, tmem_base);
@@ -220,23 +218,17 @@ int capr_knrm_forward_tc(const int64_t* query, const int64_t* doc, int B, int Q,
   // CAPR_SIM_RING=2 forces the default layout (A/B tests)
   const char* ring_env = getenv("CAPR_SIM_RING");
   a.pr.deep = (D > DT || (atoms >= 3 && !(ring_env && ring_env[0] == '2'))) ? 1 : 0;  // maxdoclen > 512 needs the deep layout's id arrays
-  a.pr.group_arrive = simtc::group_arrive_default();
-  a.pr.prod_warps = KT == 11 ? simtc::prod_warps_default() : 4;
-  const int n_threads = simtc::THREADS_PIPE + (a.pr.prod_warps == 8 ? 128 : 0);
   const size_t smem = simtc::smem_bytes(atoms, (size_t)(2 * simtc::POOL_WARPS * KT) * sizeof(float), a.pr.deep != 0);
   const int sms = sm_count();
   CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
   const int grid = B < sms ? B : sms;
   cudaStream_t st = (cudaStream_t)stream;
-  if (KT == 11 && a.pr.prod_warps == 8) {
-    CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<11, true><<<grid, n_threads, smem, st>>>(a);
-  } else if (KT == 11) {
+  if (KT == 11) {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<11><<<grid, n_threads, smem, st>>>(a);
+    knrm_tc_kernel<11><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   } else {
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(knrm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knrm_tc_kernel<16><<<grid, n_threads, smem, st>>>(a);
+    knrm_tc_kernel<16><<<grid, simtc::THREADS_PIPE, smem, st>>>(a);
   }
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

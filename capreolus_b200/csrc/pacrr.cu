@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(NT, 1) pacrr_kernel(const PacrrArgs a) {
 }
 
 // Engine 2: cosine tile from the tcgen05 producer (simtc.cuh); the conv/top-k/MLP epilogue is unchanged.
+// IDLE_SLEEP: the gather and MMA warps are idle most of the time here (the convolutions bound the kernel) and sleep between polls
+// of their barriers instead of spinning (tc::mbar_wait_idle).
+template <bool IDLE_SLEEP>
 __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const PacrrArgs a) {
   using namespace simtc;
   extern __shared__ unsigned char smem_raw[];
@@ -293,11 +296,11 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc_kernel(const Pacrr
   float* feat = s.extra;  // [QT][qterm]
   float* h1 = feat + QT * ((a.maxgram - a.mingram + 1) * a.kmax + (a.idf ? 1 : 0));
   float* h2 = h1 + MAX_COMBINE;
-  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP, a.pr.group_arrive);
+  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP);
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    producer_loop(s, a.pr, tid - EPI_THREADS);
+    producer_loop<IDLE_SLEEP>(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
-    mma_loop(s, a.pr, tmem_base);
+    mma_loop<IDLE_SLEEP>(s, a.pr, tmem_base);
   } else {
     uint32_t acc_phase = 0;
     int unit = 0;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(simtc::THREADS, 1) pacrr_tc3_kernel(const Pacr
     tc::mbar_init(&conv_full[0], 1);
     tc::mbar_init(&conv_full[1], 1);
   }
-  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP, a.pr.group_arrive);  // fence.mbarrier_init + __syncthreads inside
+  const uint32_t tmem_base = setup(s, tid, THREADS, MMA_WARP);  // fence.mbarrier_init + __syncthreads inside
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     producer_loop(s, a.pr, tid - EPI_THREADS);
   } else if (warp == EPI_WARPS + PROD_WARPS) {
@@ -570,7 +573,6 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
   a.kmax = kmax; a.combine = combine; a.nonlin = nonlin; a.table = tc_engine ? nullptr : (const float*)table;
   if (tc_engine) {
     a.pr = simtc::Problem{(const long long*)query, (const long long*)doc, B, Q, D, V, (const __nv_bfloat16*)table, (const __nv_bfloat16*)table_lo, pitch, E, 0};
-    a.pr.group_arrive = simtc::group_arrive_default();
   }
   a.l1w = l1w; a.l1b = l1b; a.l2w = l2w; a.l2b = l2b; a.l3w = l3w; a.l3b = l3b; a.scores = scores; a.topk_out = topk_out;
   // Stage the filter taps in constant memory (stream-ordered device-to-device copies).  The constant bank is one per device, so
@@ -622,8 +624,14 @@ static int pacrr_run(const char* fn, bool tc_engine, const int64_t* query, const
     const size_t smem = simtc::smem_bytes((pitch + simtc::ATOM_K - 1) / simtc::ATOM_K, extra_tc);
     CAPR_REQUIRE(smem <= simtc::MAX_DYN_SMEM, CAPR_ERR_UNSUPPORTED, "%s: ngrams*kmax too large for the tensor-core engine's shared memory: use capr_pacrr_forward", fn);
     CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit row offsets", fn);
-    CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pacrr_tc_kernel<<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+    const char* sleep_env = getenv("CAPR_PACRR_IDLE_SLEEP");  // A/B switch, default on
+    if (sleep_env && sleep_env[0] == '0') {
+      CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pacrr_tc_kernel<false><<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+    } else {
+      CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pacrr_tc_kernel<true><<<B < sms ? B : sms, simtc::THREADS, smem, st>>>(a);
+    }
   } else {
     const size_t smem = sim_tile_bytes(pitch) + extra;
     CAPR_CHECK_CUDA(cudaFuncSetAttribute(pacrr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

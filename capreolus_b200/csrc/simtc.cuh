@@ -108,8 +108,7 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int atoms, bool deep =
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
-__device__ __forceinline__ void prod_barrier(int n_threads = PROD_THREADS) { asm volatile("bar.sync 2, %0;" ::"r"(n_threads) : "memory"); }
-constexpr int THREADS_PIPE_MAX = (17 + 4) * 32;  // pipelined layout with 8 producer warps (warps 17-20)
+__device__ __forceinline__ void prod_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory"); }
 __device__ __forceinline__ void drain_barrier() { asm volatile("bar.sync 3, 128;" ::: "memory"); }  // epilogue warps 0,1,4,5
 
 struct Problem {
@@ -124,27 +123,7 @@ struct Problem {
   int single;               // 1: use only query buffer 0 and TMEM accumulator buffer 0 (PACRR's conv-on-tensor-cores epilogue
                             // needs the second query buffer's shared memory and half of TMEM for itself)
   int deep;                 // 1: the "deep" shared-memory layout (carve(..., true)): one query buffer, three doc stages
-  int prod_warps;           // gather-producer warps: 4 or 8 (pipelined kernels only; 0 is read as 4)
-  int group_arrive;         // how a gathered stage is published to the MMA warp (see producer_loop):
-                            //   0 = every producer thread posts cp.async.mbarrier.arrive.noinc (round 1; barrier count 128)
-                            //   1 = cp.async.commit_group per stage, cp.async.wait_group with a lag of ring-depth - 1 stages, then
-                            //       ONE plain mbarrier.arrive per producer warp (barrier count 4)
 };
-
-// Host side: CAPR_SIM_ARRIVE=group selects mode 1 for A/B runs.  Measured (round 2, same box, KNRM 100k pairs): mode 0 11.6 M
-// pairs/s, mode 1 7.7 M -- with a lag of only two stages cp.async.wait_group blocks until the copies have landed (the loaded L2
-// round trip is longer than two stages of issue), while the noinc arrive is truly asynchronous.  Mode 0 stays the default.
-inline int group_arrive_default() {
-  const char* e = getenv("CAPR_SIM_ARRIVE");
-  return (e && e[0] == 'g') ? 1 : 0;
-}
-// Producer warps of the pipelined kernels: 4 (round 1) or 8 (CAPR_SIM_PRODUCERS=8; warps 17-20 join).  A producer warp is paced by
-// the issue latency of its own cp.async (~35 cycles each) and cp.async.mbarrier.arrive.noinc (~600 cycles) instructions, not by
-// bandwidth (clock64 trace), so more warps issuing fewer copies each shorten the stage period.
-inline int prod_warps_default() {
-  const char* e = getenv("CAPR_SIM_PRODUCERS");
-  return (e && e[0] == '8') ? 8 : 4;
-}
 
 __device__ __forceinline__ int ring_depth(const Problem& pr) { return pr.deep ? MAX_D_STAGES : D_STAGES; }
 __device__ __forceinline__ bool one_qbuf(const Problem& pr) { return pr.single || pr.deep; }
@@ -152,13 +131,11 @@ __device__ __forceinline__ bool one_qbuf(const Problem& pr) { return pr.single |
 __device__ __forceinline__ int halves_of(const Problem& pr) { return (pr.D + NT_DOCS - 1) / NT_DOCS; }
 
 // Common prologue: barriers + TMEM.  Call from all threads; returns the TMEM base.
-__device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads = THREADS, int mma_warp = MMA_WARP, int group_arrive = 0, int prod_warps = PROD_WARPS) {
+__device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads = THREADS, int mma_warp = MMA_WARP) {
   const int warp = tid >> 5;
-  if (prod_warps == 0) prod_warps = PROD_WARPS;
-  const uint32_t fill_count = group_arrive ? prod_warps : prod_warps * 32;  // arrivals that publish a gathered buffer
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&s.q_full[i], fill_count);
+      tc::mbar_init(&s.q_full[i], PROD_THREADS);
       tc::mbar_init(&s.q_empty[i], 1);
       tc::mbar_init(&s.acc_full[i], 1);
       tc::mbar_init(&s.acc_empty[i], 4);  // the four draining warps
@@ -166,7 +143,7 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int tid, int nthreads =
       tc::mbar_init(&s.half_empty[i], POOL_WARPS);
     }
     for (int i = 0; i < MAX_D_STAGES; ++i) {
-      tc::mbar_init(&s.d_full[i], fill_count);
+      tc::mbar_init(&s.d_full[i], PROD_THREADS);
       tc::mbar_init(&s.d_empty[i], 1);
     }
     tc::fence_barrier_init();
@@ -193,16 +170,6 @@ __device__ __forceinline__ void teardown(const Smem& s, uint32_t tmem_base, int 
 // rows.  Rows are copied with 16-byte cp.async straight into the SWIZZLE_128B operand layout (8 lanes fetch one
 // 128-byte row segment: fully coalesced) and each thread posts cp.async.mbarrier.arrive.noinc on the stage's barrier,
 // which fires when ITS copies have landed -- the issuing thread never waits for data, so every stage is in flight.
-//
-// Round 2 (pr.group_arrive = 1, default).  The clock64 trace of the engine-3 kernel (scripts/sim3_trace.py) showed what
-// actually paces these kernels: cp.async.mbarrier.arrive.noinc blocks the issuing warp for ~600 cycles (a stage loop with every
-// copy switched off still took 620 cycles per stage) and a cp.async ~35 -- 16 copies + 1 arrive = ~1 160 cycles per 32 KB stage, 20
-// stages per pair = the ~25 k cycles per pair that round 1 read as the "L2 gather limit".  Mode 1 publishes a stage with a plain
-// mbarrier.arrive by one lane per warp: each stage is a cp.async commit group; after issuing stage s the thread waits (almost
-// always without blocking) for the group of stage s - (ring depth - 1), __syncwarp, lane 0 arrives on that stage's barrier.  The
-// MMA warp issues fence.proxy.async after its wait (the copies are generic-proxy writes, the tensor core reads through the async
-// proxy; a producer-side fence would drain every copy the thread has in flight).  No deadlock: the slot of stage s frees when the
-// MMA warp has consumed stage s - depth, whose arrival was posted while stage s - 1 was issued.
 // (This is the cp.async -> UMMA hand-off CUTLASS uses in sm100_mma_cpasync_warpspecialized.hpp.  Two alternatives were
 // measured and dropped: wait_group + fence.proxy.async + arrive serialises on the fence, 7.4 M pairs/s ceiling; TMA
 // tile::gather4 of 128-byte rows costs ~80 cycles per instruction, 2.6 M pairs/s.)
@@ -210,15 +177,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
+template <bool IDLE_SLEEP = false>
 __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, int ptid /*0..127*/) {
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int last_chunks = (pr.pitch - (atoms - 1) * ATOM_K) / 8;  // 16-byte chunks that exist in the last atom
   const int halves = halves_of(pr);
-  const int PT = (pr.prod_warps == 8 ? 8 : 4) * 32;  // producer threads
-  const int RS = PT >> 3;      // rows covered by one pass of the producer threads (16 or 32)
   const int sub = ptid & 7;    // 16-byte chunk inside the 128-byte row segment
-  const int rsub = ptid >> 3;  // 0..RS-1: this thread serves rows rsub + RS*j
-  const int nrows = NT_DOCS / RS, nqrows = 64 / RS;  // rows per thread of a doc stage (16 / 8) and of the query block (4 / 2)
+  const int rsub = ptid >> 3;  // 0..15: this thread serves rows rsub + 16*j
   uint32_t q_phase = 0, d_phase = 0;  // q_phase: one bit per buffer
   int d_stage = 0, it = 0;
   const int nst = ring_depth(pr);
@@ -232,68 +197,30 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
     q_next = (have && ptid < pr.Q) ? pr.q[(size_t)pair * pr.Q + ptid] : 0;  // ptid < Q <= QT
 #pragma unroll
     for (int j = 0; j < IDS_PER_THREAD; ++j) {
-      const int i = ptid + PT * j;
+      const int i = ptid + PROD_THREADS * j;
       d_next[j] = (have && i < pr.D) ? pr.d[(size_t)pair * pr.D + i] : 0;
     }
   };
   fetch_ids(blockIdx.x);
-  // mode 1: barriers of the stages whose commit groups are still in flight, oldest first (lag = ring depth - 1 = 1 or 2)
-  const bool grp = pr.group_arrive != 0;
-  const int lane = ptid & 31;
-  uint64_t* pend0 = nullptr;
-  uint64_t* pend1 = nullptr;
-  auto retire = [&](uint64_t* bar) {
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive(bar);
-  };
-  auto published = [&](uint64_t* bar) {  // the copies of a stage have been issued
-    if (!grp) {
-      cp_async_arrive_noinc(bar);
-      return;
-    }
-    cp_async_commit();
-    if (nst >= 3) {
-      if (pend0) {
-        cp_async_wait<2>();
-        retire(pend0);
-      }
-      pend0 = pend1, pend1 = bar;
-    } else {
-      if (pend1) {
-        cp_async_wait<1>();
-        retire(pend1);
-      }
-      pend1 = bar;
-    }
-  };
-  auto flush = [&]() {
-    if (!grp) return;
-    cp_async_wait<0>();
-    if (pend0) retire(pend0);
-    if (pend1) retire(pend1);
-    pend0 = pend1 = nullptr;
-  };
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = one_qbuf(pr) ? 0 : (it & 1);
-    prod_barrier(PT);  // every producer thread is done reading the previous pair's rows
+    prod_barrier();  // every producer thread is done reading the previous pair's rows
     if (ptid < QT) s.qrow[ptid] = table_row(q_next, pr.V);
 #pragma unroll
     for (int j = 0; j < IDS_PER_THREAD; ++j) {
-      const int i = ptid + PT * j;
+      const int i = ptid + PROD_THREADS * j;
       if (i < halves * NT_DOCS) s.drow[i] = table_row(d_next[j], pr.V);
     }
-    prod_barrier(PT);
+    prod_barrier();
     fetch_ids(pair + gridDim.x);
     // query block: per atom a 64-row tile, rows 0-31 = hi plane, rows 32-63 = lo plane of the 32 query tokens
-    if (one_qbuf(pr)) flush();  // the single query buffer frees when the MMA warp has finished the previous pair: publish its last stages
-    tc::mbar_wait(&s.q_empty[b], ((q_phase >> b) & 1) ^ 1);
+    tc::mbar_wait_idle<IDLE_SLEEP>(&s.q_empty[b], ((q_phase >> b) & 1) ^ 1);
     q_phase ^= 1u << b;
     {
       const uint32_t qbase = tc::smem_u32(s.qbuf(b));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j >= nqrows) break;
-        const int r = rsub + RS * j;  // 0..63
+        const int r = rsub + 16 * j;  // 0..63
         const int trow = s.qrow[r & 31];
         const __nv_bfloat16* src = (r < 32 ? pr.hi : pr.lo) + (size_t)trow * pr.pitch + sub * 8;
         const uint32_t dst = qbase + r * 128 + ((sub ^ (r & 7)) << 4);
@@ -303,7 +230,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a * Q_ATOM_BYTES), "l"(src + a * ATOM_K), "r"(nbytes) : "memory");
       }
     }
-    published(&s.q_full[b]);
+    cp_async_arrive_noinc(&s.q_full[b]);
     for (int h = 0; h < halves; ++h) {
       // Rows of <pad> / OOV tokens (table row 0) are not read at all: cp.async with src-size 0 zero-fills the 16 bytes.  Their
       // cosine is exactly 0 whatever emb[0] holds (the reference masks them, common.py:149-153), ragged batches only gather
@@ -312,7 +239,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
       unsigned live = 0;  // bit j: row j is a real table row
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int trow = j < nrows ? s.drow[h * NT_DOCS + rsub + RS * j] : 0;
+        const int trow = s.drow[h * NT_DOCS + rsub + 16 * j];
         off[j] = (unsigned)trow * (unsigned)pr.pitch + (unsigned)(sub * 8);
         live |= (trow != 0 ? 1u : 0u) << j;
       }
@@ -320,25 +247,23 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const __nv_bfloat16* tab = (plane == 0 ? pr.hi : pr.lo) + a * ATOM_K;
-          tc::mbar_wait(&s.d_empty[d_stage], d_phase ^ 1);
+          tc::mbar_wait_idle<IDLE_SLEEP>(&s.d_empty[d_stage], d_phase ^ 1);
           const uint32_t base = tc::smem_u32(s.dbuf(d_stage));
           if ((a + 1 < atoms || sub < last_chunks) && !CAPR_DBG(pr.debug & 0x800)) {  // tail chunks of a partial last atom are never read
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (j >= nrows) break;
-              const int r = rsub + RS * j;
+              const int r = rsub + 16 * j;
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
                            "r"(((live >> j) & 1u) << 4)
                            : "memory");
             }
           }
-          published(&s.d_full[d_stage]);
+          cp_async_arrive_noinc(&s.d_full[d_stage]);
           if (++d_stage == nst) d_stage = 0, d_phase ^= 1;
         }
       }
     }
   }
-  flush();
   cp_async_commit();
   cp_async_wait<0>();  // nothing may still be landing in shared memory when the CTA tears down
 }
@@ -347,6 +272,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 // Keeping the control flow warp-uniform lets ptxas hold descriptors / addresses in uniform registers; issuing from a
 // divergent `if (lane == 0)` region instead costs ~150 cycles per tcgen05.mma (R2UR chains + a serialising
 // ELECT/BRA.U.ANY loop around every UTCHMMA).
+template <bool IDLE_SLEEP = false>
 __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint32_t tmem_base) {
   const int atoms = (pr.pitch + ATOM_K - 1) / ATOM_K;
   const int halves = halves_of(pr);
@@ -357,13 +283,12 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
   const int nst = ring_depth(pr);
   for (int pair = blockIdx.x; pair < pr.B; pair += gridDim.x, ++it) {
     const int b = one_qbuf(pr) ? 0 : (it & 1);
-    tc::mbar_wait(&s.q_full[b], (q_phase >> b) & 1);
+    tc::mbar_wait_idle<IDLE_SLEEP>(&s.q_full[b], (q_phase >> b) & 1);
     q_phase ^= 1u << b;
-    if (pr.group_arrive) tc::fence_proxy_async();  // generic-proxy cp.async writes -> the tensor core's async-proxy reads
     const uint64_t q_desc = tc::make_sw128_kmajor_desc(tc::smem_u32(s.qbuf(b)));
     for (int h = 0; h < halves; ++h, ++unit) {
       const int ab = pr.single ? 0 : (unit & 1);
-      tc::mbar_wait(&s.acc_empty[ab], ((acc_phase >> ab) & 1) ^ 1);
+      tc::mbar_wait_idle<IDLE_SLEEP>(&s.acc_empty[ab], ((acc_phase >> ab) & 1) ^ 1);
       acc_phase ^= 1u << ab;
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
@@ -372,8 +297,7 @@ __device__ __forceinline__ void mma_loop(const Smem& s, const Problem& pr, uint3
         const int ksteps = skip ? 0 : min(ATOM_K, pr.pitch - a * ATOM_K) / 16;  // a partial last atom has fewer K steps
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
-          tc::mbar_wait(&s.d_full[d_stage], d_phase);
-          if (pr.group_arrive) tc::fence_proxy_async();
+          tc::mbar_wait_idle<IDLE_SLEEP>(&s.d_full[d_stage], d_phase);
           tc::tc_fence_after();
           const uint64_t bd = tc::make_sw128_kmajor_desc(tc::smem_u32(s.dbuf(d_stage)));
           if (tc::elect_one()) {
@@ -467,11 +391,9 @@ __device__ __forceinline__ void drain_pair(const Smem& s, const Problem& pr, uin
 // producers 10,14; SMSP3 = pool 3,7 + producers 11,15.
 __device__ __forceinline__ bool is_drain_warp(int warp) { return warp < 8 && (warp & 2) == 0; }
 __device__ __forceinline__ bool is_pool_warp(int warp) { return warp < 16 && ((warp < 8) == ((warp & 2) != 0)); }
-__device__ __forceinline__ bool is_producer_warp(int warp, int prod_warps = PROD_WARPS) {
-  return (warp >= 8 && warp < 16 && (warp & 2) != 0) || (prod_warps == 8 && warp >= 17 && warp < 21);
-}
+__device__ __forceinline__ bool is_producer_warp(int warp) { return warp >= 8 && warp < 16 && (warp & 2) != 0; }
 __device__ __forceinline__ int pool_index(int warp) { return (warp >> 2) * 2 + (warp & 1); }      // 2,3,6,7,8,9,12,13 -> 0..7
-__device__ __forceinline__ int producer_index(int warp) { return warp >= 17 ? 4 + (warp - 17) : ((warp - 8) >> 2) * 2 + (warp & 1); }  // 10,11,14,15 -> 0..3; 17..20 -> 4..7
+__device__ __forceinline__ int producer_index(int warp) { return ((warp - 8) >> 2) * 2 + (warp & 1); }  // 10,11,14,15 -> 0..3
 __device__ __forceinline__ float* half_tile(const Smem& s, int hb) { return s.sim + hb * HALF_FLOATS; }
 __device__ __forceinline__ float* spare_scratch(const Smem& s) { return s.sim + 2 * HALF_FLOATS; }
 

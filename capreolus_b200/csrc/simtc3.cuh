@@ -282,10 +282,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int r = rsub + 16 * j;
-              if (r < n16 && !CAPR_DBG(pr.debug & 4))
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
-                             "r"(((live >> j) & 1u) << 4)
-                             : "memory");
+              cp_async16_pred(base + r * 128 + ((sub ^ (r & 7)) << 4), tab + off[j], ((live >> j) & 1u) << 4, r < n16 && !CAPR_DBG(pr.debug & 4));
             }
           }
         }

@@ -72,6 +72,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Wait with a sleep between polls.  For warps that are idle for MICROSECONDS at a time (the gather / MMA warps of a kernel whose
+// epilogue is the bottleneck, e.g. PACRR's convolutions): a spinning try_wait loop still takes issue slots from the arithmetic warps
+// of its scheduler (25 % of PACRR's executed instructions in the round-1 profile); a sleeping warp takes none.
+template <bool SLEEP>
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  if constexpr (!SLEEP) {
+    mbar_wait(bar, parity);
+  } else {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(200);
+  }
+  }
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

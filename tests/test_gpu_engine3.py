@@ -110,15 +110,11 @@ def test_engine3_matches_oracle_identity_prepass_and_engine2(B, Q, D, V, E, monk
         monkeypatch.delenv("CAPR_SIM3_QBUFS")
         monkeypatch.setattr(common, "ENGINE", "tc")
         e2 = rr.test(gpu).cpu().numpy()
-        monkeypatch.setenv("CAPR_SIM_ARRIVE", "noinc")  # engine 2 with the round-1 stage hand-off (per-thread cp.async.mbarrier.arrive.noinc)
-        e2_noinc = rr.test(gpu).cpu().numpy()
-        monkeypatch.delenv("CAPR_SIM_ARRIVE")
     assert rel_err(got, want) < TOL
     assert np.array_equal(got, again)  # bit-reproducible
     assert np.array_equal(got, one_q)  # the layout does not change the arithmetic
     assert rel_err(ident, want) < TOL
     assert rel_err(got, e2, floor=1e-3) < 1e-4  # both engines sit ~1e-6 from the reference
-    assert np.array_equal(e2, e2_noinc)  # the hand-off protocol does not change the arithmetic
 
 
 def test_engine3_variants_and_features(monkeypatch):
@@ -156,6 +152,9 @@ def test_engine3_shards_and_chunked_workspace_are_bitwise_identical(monkeypatch)
     B, Q, D, V, E = 700, 32, 512, 3000, 300
     table = synthetic.embedding_table(V, E, seed=0)
     gpu = {k: torch.from_numpy(v).to(DEV) for k, v in synthetic.throughput_batch(B, Q, D, V, seed=5).items()}
+    gpu["posdoc"][5, 100:] = 0  # ragged documents: fewer distinct tokens than a unit holds / a single token / nothing
+    gpu["posdoc"][6, 1:] = 0
+    gpu["posdoc"][7, :] = 0
     rr, model = _knrm(table, Q, D)
     model.to(DEV)
     with torch.no_grad():
