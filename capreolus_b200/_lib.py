@@ -15,7 +15,7 @@ LIB_NAME = "libcapr_b200.so"
 LIB_PATH = Path(os.environ.get("CAPR_B200_LIB", Path(__file__).resolve().parent / LIB_NAME))
 #: debug build of the same sources (-DCAPR_DEBUG_BUILD) + the micro-benchmarks; loaded only by dbg_lib() (tests, scripts, the
 #: L2-gather roofline probe of bench.py).  Setting CAPR_B200_LIB to it makes the profiling switches (CAPR_DEBUG_FLAGS ...) live.
-DBG_LIB_PATH = Path(__file__).resolve().parent / "libcapr_b200_dbg.so"
+DBG_LIB_PATH = Path(os.environ.get("CAPR_B200_DBG_LIB", Path(__file__).resolve().parent / "libcapr_b200_dbg.so"))
 
 CAPR_OK, BAD_SHAPE, BAD_POINTER, UNSUPPORTED, CUDA_ERROR, NO_DEVICE = 0, -1, -2, -3, -4, -5
 
@@ -98,6 +98,7 @@ DEBUG_SIGNATURES = {
     "capr_debug_ffma2_bench": (c_int, [c_int, c_int, c_int, _f32p, c_void_p, c_void_p]),
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
     "capr_debug_gather_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "capr_debug_gather_bench2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -55,6 +55,14 @@ struct DeviceGuard {
 };
 int device_of(const void* device_ptr);  // -1: not a device pointer (or null)
 
+// The row gathers of the KNRM-family producers.  .cg (default) keeps the rows out of L1; -DCAPR_GATHER_CA builds the A/B variant that
+// lets L1 keep them (hot zipf rows; measured, see DESIGN.md "What limits the gather").
+#ifdef CAPR_GATHER_CA
+#define CAPR_GATHER_CP "cp.async.ca.shared.global"
+#else
+#define CAPR_GATHER_CP "cp.async.cg.shared.global"
+#endif
+
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -72,7 +80,7 @@ __device__ __forceinline__ void cp_async16_pred(uint32_t smem_dst, const void* g
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %3, 0;\n\t"
-      "@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}\n" ::"r"(smem_dst),
+      "@p " CAPR_GATHER_CP " [%0], [%1], 16, %2;\n\t}\n" ::"r"(smem_dst),
       "l"(gmem_src), "r"(nbytes), "r"((uint32_t)pred)
       : "memory");
 }

@@ -253,7 +253,7 @@ __device__ __forceinline__ void producer_loop(const Smem& s, const Problem& pr, 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int r = rsub + 16 * j;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
+              asm volatile(CAPR_GATHER_CP " [%0], [%1], 16, %2;" ::"r"(base + r * 128 + ((sub ^ (r & 7)) << 4)), "l"(tab + off[j]),
                            "r"(((live >> j) & 1u) << 4)
                            : "memory");
             }

@@ -13,6 +13,15 @@
  *     the duration of the enqueued work only;
  *   - every function returns CAPR_OK or a negative capr_status; capr_last_error() gives the text for
  *     the calling thread.  No function falls back to a CPU path.
+ *
+ * Multi-GPU.  Every entry point works on the device that owns its buffers (a device guard switches to it
+ * for the call) and knows nothing about other ranks: pairs are independent, so a caller shards the
+ * candidate list, calls the same entry point once per rank on its slice and concatenates the scores.  That
+ * one collective -- an all-gather of ceil(N/R) floats per rank, <= 500 KB at BASELINE.json configs[3] -- is
+ * DELIBERATELY host-side (capreolus_b200/sharding.py: torch.distributed.all_gather_into_tensor over NCCL)
+ * and not part of this ABI: it is latency-bound, follows the last kernel of the step and has nothing to
+ * overlap with, and keeping it out keeps the library free of an NCCL / communicator dependency (the
+ * reference has no multi-GPU scoring path to mirror; DESIGN.md section 8, measured cost 0.05 ms per step).
  */
 #ifndef CAPR_B200_H_
 #define CAPR_B200_H_
@@ -321,6 +330,10 @@ int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long l
  * stages in flight per SM.  The caller times the launch; bytes moved = (n_rows rounded down to 128) * pitch * 2 planes * 2 B. */
 int capr_debug_gather_bench(const void* table_hi, const void* table_lo, int V, int pitch, const int32_t* rows, int n_rows, int stages,
                             capr_stream_t stream);
+/* Same measurement with the hand-off variants side by side: mode bit 0 = WARP-OWNED stages (one producer warp fills a whole
+ * stage: 32 cp.async.mbarrier.arrive.noinc per stage instead of 128), bit 1 = no copies (hand-off skeleton only).  stages: 4, 8, 12. */
+int capr_debug_gather_bench2(const void* table_hi, const void* table_lo, int V, int pitch, const int32_t* rows, int n_rows, int stages, int mode,
+                             capr_stream_t stream);
 #endif /* CAPR_DEBUG_BUILD */
 
 #ifdef __cplusplus
