@@ -41,9 +41,9 @@ PARADE_P, PARADE_L = 4, 163  # PARADE: the 512-token document as 4 passages of 1
 # per layer 2*12*768^2*512 (Linear layers) + 2*2*512^2*768 (attention) = 8.05 GFLOP; x12 layers = 96.6 GFLOP
 BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
 MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM", "parade": "PTParade"}
-DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1024, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512, "parade": 1024}
+DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1184, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512, "parade": 1024}
 # pairs per H2D chunk of the end-to-end pipeline: multiples of the 148 SMs for the persistent one-CTA-per-SM kernels (no ragged last wave)
-DEFAULT_CHUNK = {"knrm": 6_216, "drmm": 12_432, "pacrr": 12_432, "bert": 256, "drmmtks": 12_432, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
+DEFAULT_CHUNK = {"knrm": 6_216, "drmm": 12_432, "pacrr": 12_432, "bert": 296, "drmmtks": 12_432, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
 TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm2_kernel<3> (+ attention_tc4_kernel)",
               "cedrknrm": "gemm2_kernel<3> (+ attention_tc4_kernel, cedr_pool_kernel)", "parade": "gemm2_kernel<3> (+ attention_tc4_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
@@ -151,7 +151,7 @@ def workload_text(model_key, n):
 def config_block(model_key, n, world):
     """`config` of the JSON line -- identical in this arm and in `--impl reference` (which times a bounded sample of the same workload)."""
     if model_key in ENCODERS:
-        l2 = "activations of one 128-sequence chunk (~2 GB) exceed L2; weights (0.35 GB as bf16 hi/lo planes) stream from HBM/L2"
+        l2 = "activations of one 296-sequence encoder call (~5 GB) exceed L2; weights (0.35 GB as bf16 hi/lo planes) stream from HBM/L2"
     else:
         l2 = "inputs larger than L2 (435 MB of ids per step); the 36 MB embedding table is L2-resident by design"
     return {"workload": workload_text(model_key, n), "pairs_per_gpu": n, "l2_policy": l2,
@@ -466,9 +466,12 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
                 "algorithmic_flops_per_pair": flops_pair, "issued_tensor_flops_per_pair": 3 * flops_pair, "issued_frac": 3 * achieved / pk["tensor"],
                 "note": "achieved counts ALGORITHMIC flops over the whole forward; the bf16x3 parity mode issues 3 tensor-core products per "
                         "algorithmic flop (Linear layers and attention), so frac is capped at 0.33; issued_frac = 3 x frac", "forward_ms": kernel_ms, "pairs_per_forward": n}
-        chunks = (n + 127) // 128
+        from capreolus_b200.reranker.ptBERTMaxP import default_seqs_per_call
+
+        spc = default_seqs_per_call()  # sequences per encoder call
+        chunks = (n + spc - 1) // spc
         launches = steps * ((2 + 12 * 7 + 1) * chunks if model_key == "bert" else (1 + 12 * 7 + 4) * chunks if model_key == "cedrknrm"
-                            else (1 + 12 * 7 + 3 + 2 * 7) * ((n * PARADE_P + 127) // 128))
+                            else (1 + 12 * 7 + 3 + 2 * 7) * ((n * PARADE_P + spc - 1) // spc))
     else:
         achieved = ALGO_BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
         traffic, tsrc = None, None
@@ -594,11 +597,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="score", choices=["score", "train"])
     ap.add_argument("--model", default="knrm", choices=sorted(MODELS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: 100k for KNRM/DRMM/PACRR = configs[1], 1024 for BERT)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: 100k for KNRM/DRMM/PACRR = configs[1], 1184 = 4 encoder calls of 296 sequences for BERT)")
     ap.add_argument("--chunk", type=int, default=0, help="pairs per H2D chunk of the end-to-end pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the monoBERT `secondary` block of the default (KNRM) line")
-    ap.add_argument("--secondary-pairs", type=int, default=1024, help="monoBERT pairs per GPU per step in the `secondary` block")
+    ap.add_argument("--secondary-pairs", type=int, default=1184, help="monoBERT pairs per GPU per step in the `secondary` block")
     ap.add_argument("--warmup-pairs", type=int, default=0, help="run the warm-up steps on the first N pairs only (full-size single-step runs, e.g. configs[3])")
     ap.add_argument("--skip-e2e", action="store_true", help="device-resident timing only (profile runs of the full-size configs; the driver's default line keeps e2e)")
     args = ap.parse_args()

@@ -15,7 +15,7 @@ from capreolus_b200 import _lib
 from capreolus_b200.module import ConfigOption, Dependency
 from capreolus_b200.reranker import Reranker
 from capreolus_b200.reranker.common import RbfKernelBank
-from capreolus_b200.reranker.ptBERTMaxP import BertEngine
+from capreolus_b200.reranker.ptBERTMaxP import BertEngine, default_seqs_per_call
 
 _CLS = {None: 0, "avg": 1, "max": 2}
 
@@ -99,7 +99,7 @@ class CEDRKNRM_Class(nn.Module):
         self.one = nn.Parameter(torch.ones(1), requires_grad=False)
         self.zero = nn.Parameter(torch.zeros(1), requires_grad=False)
         self.precision = config.get("precision", "bf16x3") if hasattr(config, "get") else "bf16x3"
-        self.max_seqs_per_call = 128
+        self.max_seqs_per_call = default_seqs_per_call()
         self._engine, self._engine_key, self._head_ws = None, None, None
 
     def engine(self) -> BertEngine:

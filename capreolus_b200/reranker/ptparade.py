@@ -12,7 +12,7 @@ from torch import nn
 from capreolus_b200 import _lib
 from capreolus_b200.module import ConfigOption, Dependency
 from capreolus_b200.reranker import Reranker
-from capreolus_b200.reranker.ptBERTMaxP import BertEngine
+from capreolus_b200.reranker.ptBERTMaxP import BertEngine, default_seqs_per_call
 
 
 class PTParade_Class(nn.Module):
@@ -59,7 +59,7 @@ class PTParade_Class(nn.Module):
         else:
             raise ValueError(f"unknown aggregation type: {self.config['aggregation']}")
         self.precision = config.get("precision", "bf16x3") if hasattr(config, "get") else "bf16x3"
-        self.max_seqs_per_call = 128
+        self.max_seqs_per_call = default_seqs_per_call()
         self._engine, self._engine_key, self._agg, self._agg_key, self._ws = None, None, None, None, None
 
     @staticmethod
