@@ -99,6 +99,7 @@ DEBUG_SIGNATURES = {
     "capr_gemm_test": (c_int, [_f32p, _f32p, _f32p, c_int, c_int, c_int, c_int, _f32p, c_void_p]),
     "capr_debug_gather_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "capr_debug_gather_bench2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "capr_debug_gather_bench3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -144,6 +144,61 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gather_bench_owned_kernel(const
   }
 }
 
+
+// How does the gather rate scale with the number of PRODUCER WARPS?  Lock-step stages, PW warps (4, 8 or 16) share the 128 rows of a
+// stage (128 / (4 PW) rows per thread).  If a warp's LDGSTS issue latency (~40 cycles per instruction in the traces) is the limit,
+// the rate grows with PW; if an SM-wide unit is, it does not.
+template <int PW>
+__global__ void __launch_bounds__(PW * 32 + 32, 1) gather_bench_warps_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int pitch,
+                                                                              const int* __restrict__ rows, int n_units, int n_stages) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[16], empty[16];
+  constexpr int RS = PW * 4;        // rows covered by one pass of the producer threads
+  constexpr int RPT = 128 / RS;     // rows per thread
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int atoms = (pitch + 63) / 64;
+  const int last_chunks = (pitch - (atoms - 1) * 64) / 8;
+  if (tid == 0) {
+    for (int i = 0; i < n_stages; ++i) tc::mbar_init(&full[i], PW * 32), tc::mbar_init(&empty[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const int per_unit = 2 * atoms;
+  if (warp < PW) {
+    const int sub = tid & 7, rsub = tid >> 3;
+    int i = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      unsigned off[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) off[j] = (unsigned)rows[(size_t)u * 128 + rsub + RS * j] * (unsigned)pitch + (unsigned)(sub * 8);
+      for (int s2 = 0; s2 < per_unit; ++s2, ++i) {
+        const int a = s2 >> 1, slot = i % n_stages;
+        const __nv_bfloat16* tab = ((s2 & 1) == 0 ? hi : lo) + a * 64;
+        tc::mbar_wait(&empty[slot], (uint32_t)(((i / n_stages) & 1) ^ 1));
+        const uint32_t base = tc::smem_u32(ring + slot * GB_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = rsub + RS * j;
+          cp_async16_pred(base + r * 128 + ((sub ^ (r & 7)) << 4), tab + off[j], 16u, a + 1 < atoms || sub < last_chunks);
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&full[slot])) : "memory");
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    int i = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x)
+      for (int s2 = 0; s2 < per_unit; ++s2, ++i) {
+        const int slot = i % n_stages;
+        tc::mbar_wait(&full[slot], (uint32_t)((i / n_stages) & 1));
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[slot]);
+      }
+  }
+}
+
 }  // namespace capr
 
 using namespace capr;
@@ -189,5 +244,33 @@ extern "C" int capr_debug_gather_bench2(const void* table_hi, const void* table_
   gather_bench_owned_kernel<<<n_units < grid ? n_units : grid, GB_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch,
                                                                                                      rows, n_units, stages, (mode >> 1) & 1, (mode & 1) ? 0 : 1);
   CAPR_CHECK_CUDA(cudaGetLastError());
+  return CAPR_OK;
+}
+
+// prod_warps: 4, 8 or 16 producer warps sharing every stage (lock-step); stages: 2..12 x 16 KB.
+extern "C" int capr_debug_gather_bench3(const void* table_hi, const void* table_lo, int V, int pitch, const int* rows, int n_rows, int stages, int prod_warps,
+                                        capr_stream_t stream) {
+  capr::DeviceGuard device_guard(table_hi);
+  const char* fn = "capr_debug_gather_bench3";
+  CAPR_REQUIRE(table_hi && table_lo && rows, CAPR_ERR_BAD_POINTER, "%s: null pointer", fn);
+  CAPR_REQUIRE(V > 0 && pitch > 0 && pitch % 16 == 0 && pitch <= 320 && n_rows >= 128 && stages >= 2 && stages <= 12, CAPR_ERR_BAD_SHAPE,
+               "%s: bad arguments V=%d pitch=%d n_rows=%d stages=%d", fn, V, pitch, n_rows, stages);
+  CAPR_REQUIRE(prod_warps == 4 || prod_warps == 8 || prod_warps == 16, CAPR_ERR_BAD_SHAPE, "%s: prod_warps=%d (4, 8 or 16)", fn, prod_warps);
+  CAPR_REQUIRE((long long)V * pitch < (1ll << 31), CAPR_ERR_UNSUPPORTED, "%s: table too large for 32-bit offsets", fn);
+  const int sms = sm_count();
+  CAPR_REQUIRE(sms > 0, CAPR_ERR_NO_DEVICE, "%s: no CUDA device", fn);
+  const size_t smem = 1024 + (size_t)stages * GB_STAGE_BYTES;
+  const int n_units = n_rows / 128;
+  const int grid = n_units < sms ? n_units : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto launch = [&](auto kernel, int threads) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, threads, smem, st>>>((const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, pitch, rows, n_units, stages);
+    return cudaGetLastError();
+  };
+  if (prod_warps == 4) CAPR_CHECK_CUDA(launch(gather_bench_warps_kernel<4>, 4 * 32 + 32));
+  else if (prod_warps == 8) CAPR_CHECK_CUDA(launch(gather_bench_warps_kernel<8>, 8 * 32 + 32));
+  else CAPR_CHECK_CUDA(launch(gather_bench_warps_kernel<16>, 16 * 32 + 32));
   return CAPR_OK;
 }

@@ -334,6 +334,9 @@ int capr_debug_gather_bench(const void* table_hi, const void* table_lo, int V, i
  * stage: 32 cp.async.mbarrier.arrive.noinc per stage instead of 128), bit 1 = no copies (hand-off skeleton only).  stages: 4, 8, 12. */
 int capr_debug_gather_bench2(const void* table_hi, const void* table_lo, int V, int pitch, const int32_t* rows, int n_rows, int stages, int mode,
                              capr_stream_t stream);
+/* ... and with 4, 8 or 16 producer warps sharing every stage (is the gather limited per warp or per SM?). */
+int capr_debug_gather_bench3(const void* table_hi, const void* table_lo, int V, int pitch, const int32_t* rows, int n_rows, int stages, int prod_warps,
+                             capr_stream_t stream);
 #endif /* CAPR_DEBUG_BUILD */
 
 #ifdef __cplusplus
