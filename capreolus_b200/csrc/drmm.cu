@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmm_tc_kernel(const D
     mma_loop(s, a.pr, tmem_base);
   } else if (is_drain_warp(warp)) {
     drain_loop(s, a.pr, tmem_base, warp, lane);
-  } else {
+  } else if (is_pool_warp(warp)) {
     const int pw = pool_index(warp), ptid = pw * 32 + lane;
     const int halves = halves_of(a.pr);
     if (ptid < a.nbins) ub[ptid] = a.bin_ub[ptid];

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) drmmtks_tc_kernel(cons
     mma_loop(s, a.pr, tmem_base);
   } else if (is_drain_warp(warp)) {
     drain_loop(s, a.pr, tmem_base, warp, lane);
-  } else {
+  } else if (is_pool_warp(warp)) {
     const int pw = pool_index(warp);
     constexpr int SLICE = NT_DOCS / POOL_WARPS;  // 32 columns per warp and half tile
     static_assert(T <= SLICE, "a warp parks its k best values of a row in its own 32-column slice");

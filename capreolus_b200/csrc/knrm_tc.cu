@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(simtc::THREADS_PIPE, 1) knrm_tc_kernel(const K
     mma_loop(s, a.pr, tmem_base);
   } else if (is_drain_warp(warp)) {
     drain_loop(s, a.pr, tmem_base, warp, lane);
-  } else {
+  } else if (is_pool_warp(warp)) {
     // ===================== pooling: 8 warps; lane = query row, warp = a 32-column slice of every half tile ============
     // Each thread keeps the K running sums of ITS row over ITS columns (K + 1 accumulators, no shuffles in the loop; the
     // one-row-per-lane float4 reads are conflict-free like the drain's stores).  At the end of the pair the 8 column

@@ -48,9 +48,13 @@ constexpr int MAX_D_STAGES = 3;               // "deep" layout: one query buffer
 constexpr int ACC_COLS = NT_DOCS;             // TMEM columns per accumulator buffer
 constexpr size_t MAX_DYN_SMEM = 232448;       // 227 KB
 constexpr int POOL_WARPS = 8;                 // pipelined epilogue: pooling warps
-constexpr int THREADS_PIPE = THREADS + 4 * 32;  // 17 warps
+#ifndef CAPR_MMA_WARP_PIPE
+#define CAPR_MMA_WARP_PIPE 16
+#endif
+constexpr int MMA_WARP_PIPE = CAPR_MMA_WARP_PIPE;  // pipelined layout: 16 (scheduler 0, next to two drain and two pooling warps) or, A/B, 18
+                                                   // (scheduler 2, next to two producer and two pooling warps; warps 16 and 17 then idle)
+constexpr int THREADS_PIPE = (MMA_WARP_PIPE + 1) * 32;  // 17 warps
 constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;  // sequential layout (PACRR)
-constexpr int MMA_WARP_PIPE = 16;                // pipelined layout
 constexpr int HALF_PITCH = NT_DOCS + 4;       // 260 floats: one-row-per-lane float4 stores are conflict-free (260 % 32 == 4)
 constexpr int HALF_FLOATS = QT * HALF_PITCH;  // one half tile = 33 280 B; two of them fit in the full-tile region
 constexpr int SPARE_FLOATS = SIM_ROWS * SIM_PITCH - 2 * HALF_FLOATS;  // 1 936 floats left over there (DRMM counters)
