@@ -43,7 +43,8 @@ BERT_FLOPS_PER_PAIR = 12 * (2 * 12 * 768 * 768 * 512 + 2 * 2 * 512 * 512 * 768)
 MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP", "drmmtks": "DRMMTKS", "convknrm": "ConvKNRM", "cedrknrm": "CEDRKNRM", "parade": "PTParade"}
 DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1184, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512, "parade": 1024}
 # pairs per H2D chunk of the end-to-end pipeline: multiples of the 148 SMs for the persistent one-CTA-per-SM kernels (no ragged last wave)
-DEFAULT_CHUNK = {"knrm": 6_216, "drmm": 12_432, "pacrr": 12_432, "bert": 296, "drmmtks": 12_432, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
+# (KNRM, same box, 10 steps: chunk 6 216 -> e2e 10.17 / 10.26 M pairs/s, 12 432 -> 10.48 / 10.53 M, 24 864 -> 10.60 M: fewer per-chunk launches and pipeline refills)
+DEFAULT_CHUNK = {"knrm": 24_864, "drmm": 12_432, "pacrr": 12_432, "bert": 296, "drmmtks": 12_432, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
 TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm2_kernel<3> (+ attention_tc4_kernel)",
               "cedrknrm": "gemm2_kernel<3> (+ attention_tc4_kernel, cedr_pool_kernel)", "parade": "gemm2_kernel<3> (+ attention_tc4_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
@@ -419,7 +420,7 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
             names = list(range(n))
             qs = PackedIdStore(names, t["query"].reshape(-1).numpy(), np.arange(n + 1, dtype=np.int64) * Q, idf=t["query_idf"].reshape(-1).numpy())
             ds = PackedIdStore(names, t["posdoc"].reshape(-1).numpy(), np.arange(n + 1, dtype=np.int64) * D)
-            rp = RunPredictor(PairAssembler(qs, ds, Q, D, dev), chunk=int(os.environ.get("CAPR_BENCH_PACKED_CHUNK", 4 * chunk)))  # no bulk H2D to hide: fewer, larger chunks keep the host launch loop off the critical path
+            rp = RunPredictor(PairAssembler(qs, ds, Q, D, dev), chunk=int(os.environ.get("CAPR_BENCH_PACKED_CHUNK", chunk if chunk >= 24_864 else 4 * chunk)))  # no bulk H2D to hide: fewer, larger chunks keep the host launch loop off the critical path
             idx = torch.arange(n, dtype=torch.int32).pin_memory()
             host_scores = torch.empty(n, dtype=torch.float32).pin_memory()
             for _ in range(2):
