@@ -44,7 +44,7 @@ MODELS = {"knrm": "KNRM", "drmm": "DRMM", "pacrr": "PACRR", "bert": "PTBERTMaxP"
 DEFAULT_PAIRS = {"knrm": 100_000, "drmm": 100_000, "pacrr": 100_000, "bert": 1184, "drmmtks": 100_000, "convknrm": 100_000, "cedrknrm": 512, "parade": 1024}
 # pairs per H2D chunk of the end-to-end pipeline: multiples of the 148 SMs for the persistent one-CTA-per-SM kernels (no ragged last wave)
 # (KNRM, same box, 10 steps: chunk 6 216 -> e2e 10.17 / 10.26 M pairs/s, 12 432 -> 10.48 / 10.53 M, 24 864 -> 10.60 M: fewer per-chunk launches and pipeline refills)
-DEFAULT_CHUNK = {"knrm": 24_864, "drmm": 12_432, "pacrr": 12_432, "bert": 296, "drmmtks": 12_432, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
+DEFAULT_CHUNK = {"knrm": 24_864, "drmm": 24_864, "pacrr": 12_432, "bert": 296, "drmmtks": 24_864, "convknrm": 12_500, "cedrknrm": 128, "parade": 256}
 TOP_KERNEL = {"knrm": "knrm_tc_kernel", "drmm": "drmm_tc_kernel", "pacrr": "pacrr_tc_kernel", "bert": "gemm2_kernel<3> (+ attention_tc4_kernel)",
               "cedrknrm": "gemm2_kernel<3> (+ attention_tc4_kernel, cedr_pool_kernel)", "parade": "gemm2_kernel<3> (+ attention_tc4_kernel)", "drmmtks": "drmmtks_tc_kernel", "convknrm": "knrm_tc_kernel x 9 views (+ convknrm_reps_kernel)"}
 ORACLE_FN = {"knrm": "knrm_forward", "drmm": "drmm_forward", "pacrr": "pacrr_forward", "drmmtks": "drmmtks_forward", "convknrm": "convknrm_forward"}
