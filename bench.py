@@ -485,6 +485,15 @@ def measure(model_key, ctx, n, chunk, steps, warmup, packed=True, pre_nccl=None,
                 "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "pairs_per_launch": n,
                 "note": "achieved = logical gather bytes (SURVEY.md 8d: ids + 544 gathered fp32 rows + score) / kernel time; the 36 MB table is "
                         "L2-resident, so the gather is L2->SM traffic and frac can exceed 1; `traffic` is the DRAM bytes ncu measured per launch"}
+        if model_key == "pacrr":
+            # the byte line is not what bounds PACRR: its 1x1 / 2x2 / 3x3 convolutions with 32 filters are 32 x (1 + 4 + 9) multiply-adds per cell
+            # of the 32 x 512 cosine tile = 14.7 MFLOP per pair on the fp32 pipe (FFMA2), against 148 SMs x 128 FMA/clk at the sampled clock
+            conv_flops = 2.0 * 32 * (1 + 4 + 9) * Q * D
+            peak_fp32 = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
+            got = conv_flops * n / (kernel_ms * 1e-3) / 1e12
+            roof["fp32_pipe"] = {"achieved": got, "peak": peak_fp32, "unit": "TFLOP/s", "frac": got / peak_fp32, "conv_flops_per_pair": conv_flops,
+                                 "note": "PACRR is bound by its fp32 convolutions (DESIGN.md section 3), not by bytes: this is the binding roofline; peak = 148 SMs x "
+                                         "128 FMA/clk x 2 at the SM clock sampled in the timed region"}
         launches = steps * (1 if model_key != "convknrm" else 13 * ((n + 4095) // 4096))  # ConvKNRM: zero row, 2 rep kernels, 9 views, combine per chunk
     line = {
         "metric": METRIC,

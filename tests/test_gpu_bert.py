@@ -150,3 +150,21 @@ def test_bert_cls_only_tail_matches_the_full_last_layer(monkeypatch):
     full = model.engine().logits(flat(b["pos_bert_input"]), flat(b["pos_mask"]), flat(b["pos_seg"])).cpu().numpy()
     np.testing.assert_allclose(fast, full, rtol=0, atol=2e-6 * float(np.abs(full).max()) + 1e-7)
     assert rel_err(full, g["logits"], floor=0.05 * float(np.abs(g["logits"]).max())) < 1e-3
+
+
+def test_bert_logits_do_not_depend_on_sequences_per_call():
+    """The encoder is called on chunks of ``max_seqs_per_call`` sequences (default 2 x SM count, ptBERTMaxP.default_seqs_per_call); a
+    sequence's logits are the same bits whatever chunk it lands in (every row of every GEMM / attention item is computed independently)."""
+    g, rr, model, b = _build("mid")
+    N, P, L, _ = (int(x) for x in g["shape"])
+    flat = lambda t: t.reshape(N * P, L)
+    eng = model.engine()
+    whole = eng.logits(flat(b["pos_bert_input"]), flat(b["pos_mask"]), flat(b["pos_seg"]))
+    default = eng.max_seqs_per_call
+    try:
+        for per_call in (1, 3, N * P):
+            eng.max_seqs_per_call = per_call
+            part = eng.logits(flat(b["pos_bert_input"]), flat(b["pos_mask"]), flat(b["pos_seg"]))
+            assert torch.equal(part, whole), per_call
+    finally:
+        eng.max_seqs_per_call = default

@@ -324,3 +324,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_default_sequences_per_encoder_call(monkeypatch):
+    """2 x SM count (296 on a B200; the same value without a device) unless CAPR_BERT_SEQS_PER_CALL overrides it."""
+    from capreolus_b200.reranker.ptBERTMaxP import default_seqs_per_call
+
+    monkeypatch.delenv("CAPR_BERT_SEQS_PER_CALL", raising=False)
+    n = default_seqs_per_call()
+    assert n > 0 and n % 2 == 0
+    import torch
+
+    if not torch.cuda.is_available():
+        assert n == 296
+    monkeypatch.setenv("CAPR_BERT_SEQS_PER_CALL", "37")
+    assert default_seqs_per_call() == 37
