@@ -8,6 +8,8 @@ the d/dmu, d/dsigma statistics and the hinge loss are the CUDA kernels behind ``
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from capreolus_b200.reranker.common import pair_hinge_loss, pair_softmax_loss
@@ -35,7 +37,11 @@ class PairwiseTrainer:
     def prepare(self, reranker):
         model = reranker.model.to(self.device)
         model.train()
-        self.optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=self.config["lr"])  # :205
+        params = [p for p in model.parameters() if p.requires_grad]
+        # pytorch.py:205 builds torch.optim.Adam(params, lr); `fused=True` is the same update rule as ONE kernel over all parameters instead
+        # of a foreach group per operation (the KNRM iteration is launch-bound: 27 small parameters); CAPR_TRAINER_FUSED_ADAM=0 restores the default
+        fused = os.environ.get("CAPR_TRAINER_FUSED_ADAM", "1") != "0" and all(p.is_cuda for p in params)
+        self.optimizer = torch.optim.Adam(params, lr=self.config["lr"], **({"fused": True} if fused else {}))
         return model
 
     def single_train_iteration(self, reranker, train_dataloader, cur_iter=0):
