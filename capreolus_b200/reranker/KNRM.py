@@ -149,9 +149,16 @@ class KNRM(Reranker):
         query_idf = d["query_idf"]
         query_sentence = d["query"]
         pos_sentence, neg_sentence = d["posdoc"], d["negdoc"]
+        m = self.model
+        if m.training and torch.is_grad_enabled() and not m.embedding.weight.requires_grad and pos_sentence.shape == neg_sentence.shape:
+            # training step (KNRM.py:87-94 scores the positive and the negative documents with two forward calls): one launch / one autograd node
+            # for both -- pairs are independent, so the scores are the same; the iteration is host-bound (bench.py --mode train)
+            B = pos_sentence.shape[0]
+            both = m(torch.cat([pos_sentence, neg_sentence]), torch.cat([query_sentence, query_sentence]), None).view(-1)
+            return [both[:B], both[B:]]
         return [
-            self.model(pos_sentence, query_sentence, query_idf).view(-1),
-            self.model(neg_sentence, query_sentence, query_idf).view(-1),
+            m(pos_sentence, query_sentence, query_idf).view(-1),
+            m(neg_sentence, query_sentence, query_idf).view(-1),
         ]
 
     def test(self, d):
