@@ -118,7 +118,8 @@ def test_convknrm_chunked_equals_whole(monkeypatch):
     assert torch.equal(whole, chunked)
 
 
-@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 2, 50, 16)])
+@pytest.mark.parametrize("B,Q,D,V,E", [(1, 32, 512, 3000, 300), (2, 4, 300, 1000, 300), (5, 17, 77, 400, 100), (150, 32, 64, 5000, 300), (3, 1, 2, 50, 16),
+                                       (3, 32, 800, 3000, 300), (2, 20, 1000, 2000, 300)])  # the extractor's default maxdoclen = 800; up to 1024
 def test_convknrm_fresh_shapes(B, Q, D, V, E):
     got, want = _fresh("ConvKNRM", "convknrm_forward", CONVKNRM_CFG["default"], B, Q, D, V, E, seed=71, oov=False)
     assert rel_err(got, want, floor=1e-2) < TOL
