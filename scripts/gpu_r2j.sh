@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: CAPR_SIM_ARRIVE / CAPR_SIM_PRODUCERS were A/B switches of experiments that were measured slower and then removed from the tree (profiles/README.md, round 2); the script documents how the numbers were taken.
 # engine 2 with the group-arrive stage hand-off: parity (short timeouts), then same-box A/B against the round-1 hand-off
 mkdir -p gpurun_out
 timeout 150 python -m pytest tests/test_gpu_engine3.py tests/test_gpu_parity.py -q --no-header -x -rf -k "knrm or engine3 or tf_dedup" > gpurun_out/pytest_knrm.log 2>&1; rc=$?; echo "knrm tests rc=$rc"; tail -4 gpurun_out/pytest_knrm.log

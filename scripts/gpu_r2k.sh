@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: CAPR_SIM_ARRIVE / CAPR_SIM_PRODUCERS were A/B switches of experiments that were measured slower and then removed from the tree (profiles/README.md, round 2); the script documents how the numbers were taken.
 # 8 producer warps in the engine-2 KNRM kernel: parity, then same-box A/B
 mkdir -p gpurun_out
 CAPR_SIM_PRODUCERS=8 timeout 120 python -m pytest tests/test_gpu_parity.py -q --no-header -x -rf -k "knrm" > gpurun_out/pytest_knrm_p8.log 2>&1; rc=$?; echo "knrm p8 tests rc=$rc"; tail -3 gpurun_out/pytest_knrm_p8.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: CAPR_SIM_ENGINE=tf (term-frequency documents on engine 2) was reverted after this A/B (profiles/README.md, round 2).
 # engine 3 with 32 KB stages: parity, ablation, bench
 mkdir -p gpurun_out
 timeout 150 python -m pytest tests/test_gpu_engine3.py -q --no-header -x -rf > gpurun_out/pytest_engine3.log 2>&1; rc=$?; echo "engine3 rc=$rc"; tail -3 gpurun_out/pytest_engine3.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: CAPR_SIM_ENGINE=tf (term-frequency documents on engine 2) was reverted after this A/B (profiles/README.md, round 2).
 # term-frequency documents on engine 2 (MMA warp untouched): parity, then same-box A/B against the library of commit f716625
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests/test_gpu_engine3.py tests/test_gpu_parity.py -q --no-header -x -rf -k "knrm or engine3 or tf_dedup or doclen" > gpurun_out/pytest_knrm.log 2>&1; rc=$?; echo "knrm tests rc=$rc"; tail -3 gpurun_out/pytest_knrm.log
