@@ -72,7 +72,8 @@ extern "C" int capr_debug_mma_bench(int M, int N, int n_mma, int n_acc, int reps
 namespace capr {
 __constant__ float c_ffma2_taps[64];
 
-template <int MODE>  // 0: constant-bank scalar broadcast (fma2_bcast), 1: vector-register {w,w} pairs, 2: plain FFMA (two per pair)
+template <int MODE>  // 0: constant-bank scalar broadcast (fma2_bcast), 1: vector-register {w,w} pairs, 2: plain FFMA (two per pair),
+                     // 3: mode 0 + FMNMX in PACRR's ratio (24 filter-max operations per 56 FFMA2: does the max share the FMA pipe's slots?)
 __global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float* __restrict__ gw, float* out, long long* cycles) {
   float2 acc[8];
 #pragma unroll
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float
   float wreg[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) wreg[t] = gw[t];
+  float best[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -90,8 +92,9 @@ __global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float
     for (int t = 0; t < 16; ++t) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 3) {
           acc[i] = fma2_bcast(c_ffma2_taps[t], x[i], acc[i]);
+          if (MODE == 3 && (i < 3 || (i == 3 && (t & 1) == 0))) best[i] = fmaxf(best[i], acc[(i + 4) & 7].y);  // 56 FMNMX per 128 FFMA2
         } else if (MODE == 1) {
           const float2 ww = make_float2(wreg[t], wreg[t]);
           unsigned long long rd;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+  if (MODE == 3) s += (best[0] + best[1]) + (best[2] + best[3]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -117,13 +121,14 @@ __global__ void __launch_bounds__(256) ffma2_bench_kernel(int iters, const float
 
 // cycles[grid]: SM cycles for iters x 16 taps x 8 packed FMAs per thread, 256 threads per CTA (8 warps, 2 per scheduler).
 extern "C" int capr_debug_ffma2_bench(int mode, int iters, int grid, float* scratch, long long* cycles, capr_stream_t stream) {
-  CAPR_REQUIRE(mode >= 0 && mode <= 2 && iters > 0 && grid > 0 && scratch && cycles, CAPR_ERR_BAD_SHAPE, "capr_debug_ffma2_bench: bad arguments");
+  CAPR_REQUIRE(mode >= 0 && mode <= 3 && iters > 0 && grid > 0 && scratch && cycles, CAPR_ERR_BAD_SHAPE, "capr_debug_ffma2_bench: bad arguments");
   float h[64];
   for (int i = 0; i < 64; ++i) h[i] = 1.0f + 1e-4f * i;
   CAPR_CHECK_CUDA(cudaMemcpyToSymbolAsync(capr::c_ffma2_taps, h, sizeof(h), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CAPR_CHECK_CUDA(cudaMemcpyAsync(scratch, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   if (mode == 0) capr::ffma2_bench_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
   else if (mode == 1) capr::ffma2_bench_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
+  else if (mode == 3) capr::ffma2_bench_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
   else capr::ffma2_bench_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, scratch, scratch + 64, cycles);
   CAPR_CHECK_CUDA(cudaGetLastError());
   return CAPR_OK;

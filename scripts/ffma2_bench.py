@@ -5,7 +5,8 @@ lib = _lib.dbg_lib()
 grid, iters = 148, 2000
 scratch = torch.zeros(64 + grid * 256, device="cuda")
 cyc = torch.zeros(grid, dtype=torch.int64, device="cuda")
-for mode, name in ((0, "FFMA2, constant-bank scalar (UR broadcast)"), (1, "FFMA2, vector-register pair"), (2, "plain FFMA x2")):
+for mode, name in ((0, "FFMA2, constant-bank scalar (UR broadcast)"), (1, "FFMA2, vector-register pair"), (2, "plain FFMA x2"),
+                   (3, "FFMA2 (const) + FMNMX, 56 max per 128 FFMA2")):
     for _ in range(2):
         _lib.check(lib.capr_debug_ffma2_bench(mode, iters, grid, scratch.data_ptr(), cyc.data_ptr(), None))
     torch.cuda.synchronize()
